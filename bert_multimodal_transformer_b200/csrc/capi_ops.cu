@@ -1,0 +1,169 @@
+// extern "C" boundary for the row-wise operators, attention, head, optimizer and the whole-model schedules.
+#include "common.cuh"
+#include "gemm_sm100.cuh"
+#include "host.h"
+#include "../../include/magb200.h"
+
+using namespace magb200;
+
+#define ST reinterpret_cast<cudaStream_t>(stream)
+#define RUN(expr)        \
+  do {                   \
+    int _rc = (expr);    \
+    if (_rc) return _rc; \
+  } while (0)
+
+extern "C" {
+
+int magb200_dropout_mask(uint8_t* out, int64_t n, float p, uint64_t seed, uint32_t site, void* stream) {
+  return dropout_mask(out, n, p, seed, site, ST);
+}
+
+int magb200_cast_f32_f16(const float* in, void* out_f16, int64_t n, void* stream) {
+  return cast_f32_f16(in, reinterpret_cast<__half*>(out_f16), n, ST);
+}
+
+int magb200_embed_ln_fwd(const int64_t* ids, const int64_t* token_type_ids, const float* visual, const float* acoustic,
+                         const float* word, const float* pos, const float* type, const float* gamma, const float* beta,
+                         float eps, float p, uint64_t seed, uint32_t site, int V, int A, int ka, int T, int S, int vocab,
+                         float* emb32, void* amag16, void* stream) {
+  EmbedArgs e;
+  e.ids = ids; e.tt = token_type_ids; e.visual = visual; e.acoustic = acoustic; e.word = word; e.pos = pos;
+  e.type = type; e.gamma = gamma; e.beta = beta; e.eps = eps; e.p = p; e.seed = seed; e.site = site; e.V = V; e.A = A;
+  e.KA = ka; e.T = T; e.S = S; e.vocab = vocab; e.emb32 = emb32; e.amag = reinterpret_cast<__half*>(amag16);
+  return embed_ln_fwd(e, ST);
+}
+
+int magb200_embed_ln_bwd(const float* dout, const int64_t* ids, const int64_t* token_type_ids, const float* word,
+                         const float* pos, const float* type, const float* gamma, float eps, float p, uint64_t seed,
+                         uint32_t site, int T, int S, int vocab, float out_scale, float* dword, float* dpos, float* dtype,
+                         float* dgamma, float* dbeta, void* stream) {
+  EmbedArgs e;
+  e.ids = ids; e.tt = token_type_ids; e.word = word; e.pos = pos; e.type = type; e.gamma = gamma; e.eps = eps; e.p = p;
+  e.seed = seed; e.site = site; e.T = T; e.S = S; e.vocab = vocab;
+  return embed_ln_bwd(e, dout, out_scale, dword, dpos, dtype, dgamma, dbeta, ST);
+}
+
+int magb200_mag_pack_weights(const float* W_hv, const float* W_ha, const float* W_v, const float* W_a, int V, int A,
+                             int ka, void* packed16, void* stream) {
+  return mag_pack_weights(W_hv, W_ha, W_v, W_a, V, A, ka, reinterpret_cast<__half*>(packed16), ST);
+}
+
+int magb200_mag_fwd(const float* text32, const float* visual, const float* acoustic, const void* packed16,
+                    const float* bias4, const float* ln_gamma, const float* ln_beta, float beta_shift, float ln_eps,
+                    float p, uint64_t seed, uint32_t site, int V, int A, int ka, int T, void* amag16, float* gates32,
+                    float* out32, void* out16, void* stream) {
+  const int H = 768;
+  MAGB_REQUIRE(ka == H + 128, "mag: ka must be 896");
+  RUN(mag_pack_inputs(text32, visual, acoustic, V, A, ka, T, reinterpret_cast<__half*>(amag16), ST));
+  GemmProblem g;
+  g.A = amag16; g.B = packed16; g.M = T; g.N = 4 * H; g.K = ka; g.lda = ka; g.ldb = ka;
+  g.a_dtype = DT_F16; g.b_dtype = DT_F16; g.epi = EPI_STORE_F32; g.bias = bias4; g.out0 = gates32; g.ldo = 4 * H;
+  g.n_split = 2 * H; g.k_start_hi = H;
+  RUN(gemm_launch(g, ST));
+  return mag_tail_fwd(gates32, text32, ln_gamma, ln_beta, beta_shift, ln_eps, p, seed, site, T, out32,
+                      reinterpret_cast<__half*>(out16), ST);
+}
+
+int magb200_mag_bwd(const float* dout, const float* text32, const void* amag16, const float* gates32,
+                    const void* packed16, const float* ln_gamma, float beta_shift, float ln_eps, float p, uint64_t seed,
+                    uint32_t site, int V, int A, int ka, int T, float out_scale, void* dgates16, float* dpacked32,
+                    float* dtext32, float* dW_hv, float* dW_ha, float* dW_v, float* dW_a, float* dbias4, float* dgamma, float* dbeta,
+                    void* stream) {
+  const int H = 768;
+  MAGB_REQUIRE(ka == H + 128, "mag: ka must be 896");
+  RUN(mag_tail_bwd(dout, gates32, text32, ln_gamma, beta_shift, ln_eps, p, seed, site, T, out_scale,
+                   reinterpret_cast<__half*>(dgates16), dtext32, dgamma, dbeta, dbias4, ST));
+  MAGB_CHECK_CUDA(cudaMemsetAsync(dpacked32, 0, (size_t)4 * H * ka * sizeof(float), ST));
+  GemmProblem w;  // dB[4H][ka] += dG^T * Amag
+  w.A = dgates16; w.B = amag16; w.M = 4 * H; w.N = ka; w.K = T; w.lda = 4 * H; w.ldb = ka; w.a_mn = true; w.b_mn = true;
+  w.a_dtype = DT_F16; w.b_dtype = DT_F16; w.epi = EPI_ATOMIC_F32; w.out0 = dpacked32; w.ldo = ka; w.alpha = out_scale;
+  RUN(gemm_launch(w, ST));
+  RUN(mag_unpack_wgrad(dpacked32, V, A, ka, dW_hv, dW_ha, dW_v, dW_a, ST));
+  GemmProblem d;  // dtext += dG[:, :2H] * B[:2H, :H]
+  d.A = dgates16; d.B = packed16; d.M = T; d.N = H; d.K = 2 * H; d.lda = 4 * H; d.ldb = ka; d.b_mn = true;
+  d.a_dtype = DT_F16; d.b_dtype = DT_F16; d.epi = EPI_STORE_F32; d.out0 = dtext32; d.aux = dtext32; d.ldo = H;
+  return gemm_launch(d, ST);
+}
+
+int magb200_dropout_residual_ln_fwd(const float* pre, const float* res, const float* gamma, const float* beta,
+                                    float eps, float p, uint64_t seed, uint32_t site, int T, float* y32, void* y16,
+                                    float* rstd, void* stream) {
+  return dropout_residual_ln_fwd(pre, res, gamma, beta, eps, p, seed, site, T, y32, reinterpret_cast<__half*>(y16), rstd,
+                                 ST);
+}
+
+int magb200_ln_bwd(const float* dy32, const float* y32, const float* gamma, const float* beta, const float* rstd,
+                   float p, uint64_t seed, uint32_t site, int T, float out_scale, float* dz32, void* dpre16,
+                   float* dgamma, float* dbeta, float* dbias, void* stream) {
+  return ln_bwd(dy32, y32, gamma, beta, rstd, p, seed, site, T, out_scale, dz32, reinterpret_cast<__half*>(dpre16), dgamma, dbeta,
+                dbias, ST);
+}
+
+int magb200_colsum_f16(const void* in_f16, int T, int N, float out_scale, float* out, void* stream) {
+  return colsum_f16(reinterpret_cast<const __half*>(in_f16), T, N, out_scale, out, ST);
+}
+
+int magb200_sdpa_fwd(const void* qkv16, const int64_t* mask, int B, int S, int heads, int head_dim, float p,
+                     uint64_t seed, uint32_t site, void* ctx16, void* stream) {
+  return sdpa_fwd(reinterpret_cast<const __half*>(qkv16), mask, B, S, heads, head_dim, p, seed, site,
+                  reinterpret_cast<__half*>(ctx16), ST);
+}
+
+int magb200_sdpa_bwd(const void* qkv16, const void* dctx16, const int64_t* mask, int B, int S, int heads, int head_dim,
+                     float p, uint64_t seed, uint32_t site, void* dqkv16, void* stream) {
+  return sdpa_bwd(reinterpret_cast<const __half*>(qkv16), reinterpret_cast<const __half*>(dctx16), mask, B, S, heads,
+                  head_dim, p, seed, site, reinterpret_cast<__half*>(dqkv16), ST);
+}
+
+int magb200_cls_fwd(const float* pre, const float* Wc, const float* bc, int B, int num_labels, float p, uint64_t seed,
+                    uint32_t site, float* pooled, float* logits, void* stream) {
+  return cls_fwd(pre, Wc, bc, B, num_labels, p, seed, site, pooled, logits, ST);
+}
+
+int magb200_cls_bwd(const float* dlogits, const float* pooled, const float* Wc, int B, int num_labels, float p,
+                    uint64_t seed, uint32_t site, float out_scale, void* dpre16, float* dWc, float* dbc, void* stream) {
+  return cls_bwd(dlogits, pooled, Wc, B, num_labels, p, seed, site, out_scale, reinterpret_cast<__half*>(dpre16), dWc, dbc, ST);
+}
+
+int magb200_mse_loss(const float* logits, const float* labels, int n, float grad_scale, float* loss, float* dlogits,
+                     void* stream) {
+  return mse_loss(logits, labels, n, grad_scale, loss, dlogits, ST);
+}
+
+int magb200_adamw_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* p16,
+                       const uint8_t* decay_chunk, int64_t n, float lr, float beta1, float beta2, float eps,
+                       float weight_decay, int step, float grad_unscale, int zero_grad, void* stream) {
+  return adamw_step(params, grads, exp_avg, exp_avg_sq, reinterpret_cast<__half*>(p16), decay_chunk, n, lr, beta1, beta2,
+                    eps, weight_decay, step, grad_unscale, zero_grad, ST);
+}
+
+size_t magb200_bert_workspace_bytes(const magb200_bert_dims* dims) { return bert_workspace_bytes(*dims); }
+
+int magb200_bert_refresh_operands(const magb200_bert_dims* dims, const int64_t* off, const float* params,
+                                  void* params16, void* stream) {
+  return bert_refresh_operands(*dims, off, params, reinterpret_cast<__half*>(params16), ST);
+}
+
+int magb200_bert_forward(const magb200_bert_dims* dims, const int64_t* off, const float* params, const void* params16,
+                         const int64_t* input_ids, const int64_t* token_type_ids, const int64_t* attention_mask,
+                         const float* visual, const float* acoustic, void* workspace, size_t workspace_bytes,
+                         float* logits, void* stream) {
+  return bert_forward(*dims, off, params, reinterpret_cast<const __half*>(params16), input_ids, token_type_ids,
+                      attention_mask, visual, acoustic, workspace, workspace_bytes, logits, ST);
+}
+
+int magb200_bert_backward(const magb200_bert_dims* dims, const int64_t* off, const float* params, const void* params16,
+                          const int64_t* input_ids, const int64_t* token_type_ids, const int64_t* attention_mask,
+                          void* workspace, size_t workspace_bytes, const float* dlogits_scaled, float* grads,
+                          void* stream) {
+  return bert_backward(*dims, off, params, reinterpret_cast<const __half*>(params16), input_ids, token_type_ids,
+                       attention_mask, workspace, workspace_bytes, dlogits_scaled, grads, ST);
+}
+
+int magb200_bert_peek(const magb200_bert_dims* dims, void* workspace, int what, int layer, void* out, size_t out_bytes,
+                      void* stream) {
+  return bert_peek(*dims, workspace, what, layer, out, out_bytes, ST);
+}
+
+}  // extern "C"

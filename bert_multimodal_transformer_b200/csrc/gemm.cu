@@ -1,0 +1,157 @@
+// Host side of the tcgen05 GEMM: TMA descriptor construction (cached), kernel selection, launch.
+#include "gemm_sm100.cuh"
+#include "host.h"
+
+#include <mutex>
+#include <unordered_map>
+#include <cstring>
+
+namespace magb200 {
+
+// ---------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled is a driver entry point; fetch it through the runtime so the library
+// has no link-time dependency on libcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  uint64_t d0, d1, ld;
+  uint32_t b0, b1, dt;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && ld == o.ld && b0 == o.b0 && b1 == o.b1 && dt == o.dt;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    auto mix = [&h](uint64_t v) { h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); };
+    mix(k.d0); mix(k.d1); mix(k.ld); mix(k.b0); mix(k.b1); mix(k.dt);
+    return h;
+  }
+};
+
+// 2-D row-major tensor [d1 rows][d0 contiguous], row pitch ld elements, box [b1][b0], SWIZZLE_128B.
+static int get_tensor_map(CUtensorMap* out, const void* ptr, int dtype, uint64_t d0, uint64_t d1, uint64_t ld,
+                          uint32_t b0, uint32_t b1) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{ptr, d0, d1, ld, b0, b1, (uint32_t)dtype};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  MAGB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  const uint32_t eb = dtype == DT_F32 ? 4 : 2;
+  MAGB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA operand %p is not 16-byte aligned", ptr);
+  MAGB_REQUIRE((ld * eb) % 16 == 0, "TMA operand row pitch %llu B is not a multiple of 16", (unsigned long long)(ld * eb));
+  MAGB_REQUIRE(b0 * eb == 128, "TMA box inner extent must be 128 bytes");
+  CUtensorMapDataType cdt = dtype == DT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                          : dtype == DT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                            : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  cuuint64_t gdim[2] = {d0, d1};
+  cuuint64_t gstr[1] = {ld * eb};
+  cuuint32_t box[2] = {b0, b1};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, cdt, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MAGB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) ptr=%p dims=%llux%llu ld=%llu box=%ux%u", (int)r,
+               ptr, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)ld, b0, b1);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache.emplace(key, m);
+  }
+  *out = m;
+  return 0;
+}
+
+template <int EB, bool A_MN, bool B_MN, int BN, int STAGES>
+static int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, dim3 grid, cudaStream_t st) {
+  using SM = GemmSmem<EB, A_MN, B_MN, BN, STAGES>;
+  auto kern = gemm_tcgen05_kernel<EB, A_MN, B_MN, BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    MAGB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    configured = true;
+  }
+  kern<<<grid, 192, SM::TOTAL, st>>>(ta, tb, g);
+  MAGB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int EB, int BN, int STAGES>
+static int launch_majors(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g,
+                         dim3 grid, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch_variant<EB, false, false, BN, STAGES>(ta, tb, g, grid, st);
+  if (!a_mn && b_mn) return launch_variant<EB, false, true, BN, STAGES>(ta, tb, g, grid, st);
+  if (a_mn && !b_mn) return launch_variant<EB, true, false, BN, STAGES>(ta, tb, g, grid, st);
+  return launch_variant<EB, true, true, BN, STAGES>(ta, tb, g, grid, st);
+}
+
+int gemm_launch(const GemmProblem& p, cudaStream_t st) {
+  MAGB_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem %dx%dx%d", p.M, p.N, p.K);
+  const bool a32 = p.a_dtype == DT_F32, b32 = p.b_dtype == DT_F32;
+  // measured on B200: tcgen05.mma kind::f16 traps (illegal instruction) when A and B formats differ,
+  // and kind::tf32 with MN-major operands returns wrong results with this descriptor scheme.
+  MAGB_REQUIRE(p.a_dtype == p.b_dtype, "gemm: A and B must have the same element type (f16, bf16 or f32/tf32)");
+  MAGB_REQUIRE(!(a32 && (p.a_mn || p.b_mn)), "gemm: tf32 operands must be K-major");
+  const int EB = a32 ? 4 : 2;
+  const int BK = 128 / EB, ATOM = 128 / EB, BM = 128;
+  const int BN = 128;
+  MAGB_REQUIRE(p.N % 32 == 0, "gemm: N=%d must be a multiple of 32", p.N);
+  MAGB_REQUIRE(p.ldo % 8 == 0, "gemm: ldo=%d must be a multiple of 8", p.ldo);
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (!p.a_mn) rc = get_tensor_map(&ta, p.A, p.a_dtype, p.K, p.M, p.lda, BK, BM);
+  else rc = get_tensor_map(&ta, p.A, p.a_dtype, p.M, p.K, p.lda, ATOM, BK);
+  if (rc) return rc;
+  if (!p.b_mn) rc = get_tensor_map(&tb, p.B, p.b_dtype, p.K, p.N, p.ldb, BK, BN);
+  else rc = get_tensor_map(&tb, p.B, p.b_dtype, p.N, p.K, p.ldb, ATOM, BK);
+  if (rc) return rc;
+
+  GemmArgs g;
+  g.M = p.M; g.N = p.N; g.K = p.K;
+  g.kb_total = (p.K + BK - 1) / BK;
+  int splits = p.splits < 1 ? 1 : p.splits;
+  if (splits > g.kb_total) splits = g.kb_total;
+  g.kb_per_split = (g.kb_total + splits - 1) / splits;
+  splits = (g.kb_total + g.kb_per_split - 1) / g.kb_per_split;  // no empty split
+  MAGB_REQUIRE(splits == 1 || p.epi == EPI_ATOMIC_F32, "gemm: split-K requires the atomic epilogue");
+  g.n_split = p.n_split > 0 ? p.n_split : 0x7fffffff;
+  g.kb_start_hi = p.k_start_hi / BK;
+  MAGB_REQUIRE(p.k_start_hi % BK == 0, "gemm: k_start_hi must be a multiple of the K block");
+  MAGB_REQUIRE(p.n_split <= 0 || (splits == 1 && g.kb_start_hi < g.kb_total && p.n_split % BN == 0),
+               "gemm: invalid n_split configuration");
+  g.epi = p.epi; g.bias = p.bias; g.out0 = p.out0; g.out1 = p.out1; g.aux = p.aux; g.ldo = p.ldo; g.alpha = p.alpha;
+  const uint32_t af = p.a_dtype == DT_F32 ? 2u : (p.a_dtype == DT_BF16 ? 1u : 0u);
+  const uint32_t bf = p.b_dtype == DT_F32 ? 2u : (p.b_dtype == DT_BF16 ? 1u : 0u);
+  g.idesc = make_idesc(af, bf, p.a_mn, p.b_mn, BM, BN);
+
+  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, splits);
+  if (EB == 2) return launch_majors<2, 128, 3>(p.a_mn, p.b_mn, ta, tb, g, grid, st);
+  return launch_majors<4, 128, 3>(p.a_mn, p.b_mn, ta, tb, g, grid, st);
+}
+
+}  // namespace magb200

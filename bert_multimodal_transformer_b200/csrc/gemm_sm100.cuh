@@ -1,0 +1,308 @@
+// tcgen05 GEMM for sm_100a:  D[M,N] = A[M,K] * B[N,K]^T  (+ epilogue)
+//
+//   * operands staged in shared memory by TMA (cp.async.bulk.tensor, SWIZZLE_128B),
+//   * tcgen05.mma issued by one elected thread, fp32 accumulators in TMEM,
+//   * tcgen05.ld epilogue by 4 warps (one TMEM lane quarter each), fused elementwise epilogues.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue.  One 128 x BN output tile per CTA; 2 CTAs co-reside per SM (3-stage
+// ring each) so one CTA's epilogue overlaps the other's main loop.
+//
+// Operand layouts ("major" = the contiguous dimension in global memory):
+//   A K-major : A stored [M][K]  (nn.Linear activations)       A MN-major: stored [K][M]
+//   B K-major : B stored [N][K]  (nn.Linear weight [out,in])   B MN-major: stored [K][N]
+// MN-major operands let the weight-gradient GEMM  dW[N,K] = dY[T,N]^T * X[T,K]  read dY and X in
+// place (reduction over tokens, both operands token-major) with no transposed copies.
+#pragma once
+
+#include "common.cuh"
+
+namespace magb200 {
+
+enum GemmEpilogue : int {
+  EPI_STORE_F32 = 0,    // out0(f32) = v                 [+ aux(f32) if aux != null]
+  EPI_STORE_F16 = 1,    // out0(f16) = v
+  EPI_STORE_BF16 = 2,   // out0(bf16) = v
+  EPI_GELU_F16 = 3,     // out0(f16) = gelu(v); out1(f16) = v if out1 != null
+  EPI_DGELU_F16 = 4,    // out0(f16) = v * gelu'(aux(f16))
+  EPI_ATOMIC_F32 = 5,   // out0(f32) += v   (red.global.add; split-K / gradient accumulation)
+  EPI_STORE_F32_F16 = 6,  // out0(f32) = v; out1(f16) = v
+  EPI_RELU_F32 = 7,     // out0(f32) = max(v, 0)
+};
+// v = alpha * acc + bias[n]
+
+struct GemmArgs {
+  int M, N, K;        // logical problem
+  int kb_total;       // number of K blocks
+  int kb_per_split;   // K blocks per blockIdx.z
+  int n_split;        // tiles with n0 >= n_split start at K block kb_start_hi (block-sparse B, MAG gate GEMM)
+  int kb_start_hi;
+  int epi;
+  const float* bias;
+  void* out0;
+  void* out1;
+  const void* aux;
+  int ldo;            // leading dimension (elements) of out0/out1/aux
+  float alpha;
+  uint32_t idesc;
+};
+
+template <int EB>
+struct GemmTile {
+  static constexpr int BM = 128;
+  static constexpr int BK = 128 / EB;    // elements per K block (one 128-byte swizzle row)
+  static constexpr int UK = 32 / EB;     // K per tcgen05.mma
+  static constexpr int ATOM = 128 / EB;  // MN elements per 128-byte row (MN-major)
+};
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// One thread owns 32 consecutive columns [n, n+32) of output row m.
+__device__ __forceinline__ void gemm_epilogue_row32(const GemmArgs& g, int m, int n, uint32_t (&r)[32]) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * g.alpha;
+  if (g.bias != nullptr) {
+    const float4* b4 = reinterpret_cast<const float4*>(g.bias + n);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = __ldg(b4 + j);
+      v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+    }
+  }
+  const size_t off = (size_t)m * g.ldo + n;
+  switch (g.epi) {
+    case EPI_STORE_F32:
+    case EPI_RELU_F32:
+    case EPI_STORE_F32_F16: {
+      if (g.epi == EPI_RELU_F32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (g.aux != nullptr && g.epi == EPI_STORE_F32) {
+        const float4* a4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g.aux) + off);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 a = a4[j];
+          v[4 * j + 0] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+        }
+      }
+      float* o = reinterpret_cast<float*>(g.out0) + off;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        st_global_v4(o + 4 * j, __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                     __float_as_uint(v[4 * j + 3]));
+      if (g.epi == EPI_STORE_F32_F16) {
+        __half* o1 = reinterpret_cast<__half*>(g.out1) + off;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          st_global_v4(o1 + 8 * j, pack_f16(v[8 * j], v[8 * j + 1]), pack_f16(v[8 * j + 2], v[8 * j + 3]),
+                       pack_f16(v[8 * j + 4], v[8 * j + 5]), pack_f16(v[8 * j + 6], v[8 * j + 7]));
+      }
+    } break;
+    case EPI_STORE_F16: {
+      __half* o = reinterpret_cast<__half*>(g.out0) + off;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        st_global_v4(o + 8 * j, pack_f16(v[8 * j], v[8 * j + 1]), pack_f16(v[8 * j + 2], v[8 * j + 3]),
+                     pack_f16(v[8 * j + 4], v[8 * j + 5]), pack_f16(v[8 * j + 6], v[8 * j + 7]));
+    } break;
+    case EPI_STORE_BF16: {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(g.out0) + off;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        st_global_v4(o + 8 * j, pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                     pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+    } break;
+    case EPI_GELU_F16: {
+      if (g.out1 != nullptr) {
+        __half* o1 = reinterpret_cast<__half*>(g.out1) + off;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          st_global_v4(o1 + 8 * j, pack_f16(v[8 * j], v[8 * j + 1]), pack_f16(v[8 * j + 2], v[8 * j + 3]),
+                       pack_f16(v[8 * j + 4], v[8 * j + 5]), pack_f16(v[8 * j + 6], v[8 * j + 7]));
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+      __half* o = reinterpret_cast<__half*>(g.out0) + off;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        st_global_v4(o + 8 * j, pack_f16(v[8 * j], v[8 * j + 1]), pack_f16(v[8 * j + 2], v[8 * j + 3]),
+                     pack_f16(v[8 * j + 4], v[8 * j + 5]), pack_f16(v[8 * j + 6], v[8 * j + 7]));
+    } break;
+    case EPI_DGELU_F16: {
+      const uint4* u4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(g.aux) + off);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 u = u4[j];
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[t]));
+          v[8 * j + 2 * t] *= gelu_erf_grad(f.x);
+          v[8 * j + 2 * t + 1] *= gelu_erf_grad(f.y);
+        }
+      }
+      __half* o = reinterpret_cast<__half*>(g.out0) + off;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        st_global_v4(o + 8 * j, pack_f16(v[8 * j], v[8 * j + 1]), pack_f16(v[8 * j + 2], v[8 * j + 3]),
+                     pack_f16(v[8 * j + 4], v[8 * j + 5]), pack_f16(v[8 * j + 6], v[8 * j + 7]));
+    } break;
+    case EPI_ATOMIC_F32: {
+      float* o = reinterpret_cast<float*>(g.out0) + off;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red_add_v4(o + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } break;
+    default: break;
+  }
+}
+
+template <int EB, bool A_MN, bool B_MN, int BN, int STAGES>
+struct GemmSmem {
+  using T = GemmTile<EB>;
+  static constexpr int A_BYTES = T::BM * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+};
+
+template <int EB, bool A_MN, bool B_MN, int BN, int STAGES>
+__global__ void __launch_bounds__(192, 2)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+  using T = GemmTile<EB>;
+  using SM = GemmSmem<EB, A_MN, B_MN, BN, STAGES>;
+  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
+  static_assert((BN & (BN - 1)) == 0, "TMEM allocation must be a power of two");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * T::BM;
+
+  int kb_begin = blockIdx.z * g.kb_per_split;
+  int kb_end = min(kb_begin + g.kb_per_split, g.kb_total);
+  if (n0 >= g.n_split) kb_begin = max(kb_begin, g.kb_start_hi);
+  const int num_kb = kb_end - kb_begin;   // host guarantees >= 1
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      mbar_init(tmem_full_bar, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int it = 0; it < num_kb; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], SM::STAGE_BYTES);
+        uint8_t* a_dst = smem + s * SM::STAGE_BYTES;
+        uint8_t* b_dst = a_dst + SM::A_BYTES;
+        const int k0 = (kb_begin + it) * T::BK;
+        if constexpr (!A_MN) {
+          tma_load_2d(a_dst, &tmA, &full_bar[s], k0, m0);
+        } else {
+#pragma unroll
+          for (int i = 0; i < T::BM / T::ATOM; ++i)
+            tma_load_2d(a_dst + i * (T::BK * 128), &tmA, &full_bar[s], m0 + i * T::ATOM, k0);
+        }
+        if constexpr (!B_MN) {
+          tma_load_2d(b_dst, &tmB, &full_bar[s], k0, n0);
+        } else {
+#pragma unroll
+          for (int i = 0; i < BN / T::ATOM; ++i)
+            tma_load_2d(b_dst + i * (T::BK * 128), &tmB, &full_bar[s], n0 + i * T::ATOM, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      for (int it = 0; it < num_kb; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(smem + s * SM::STAGE_BYTES);
+        const uint32_t b_base = a_base + SM::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < T::BK / T::UK; ++k) {
+          // K-major : 8-row groups 1024 B apart (SBO); K advances 32 B inside the 128-B swizzle row.
+          // MN-major: 64-element (128 B) MN atoms BK*128 B apart (LBO), 8-K-row groups 1024 B apart
+          //           (SBO); K advances UK rows = UK*128 B.
+          const uint64_t adesc = A_MN ? make_smem_desc_sw128(a_base + k * T::UK * 128, T::BK * 128, 1024)
+                                      : make_smem_desc_sw128(a_base + k * 32, 0, 1024);
+          const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_base + k * T::UK * 128, T::BK * 128, 1024)
+                                      : make_smem_desc_sw128(b_base + k * 32, 0, 1024);
+          if constexpr (EB == 2) tc_mma_f16(tmem_base, adesc, bdesc, g.idesc, (it | k) != 0);
+          else tc_mma_tf32(tmem_base, adesc, bdesc, g.idesc, (it | k) != 0);
+        }
+        tc_commit(&empty_bar[s]);  // smem slot reusable once these MMAs have read it
+      }
+      tc_commit(tmem_full_bar);    // accumulator complete
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int m = m0 + q * 32 + lane;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+      tmem_ld_wait();
+      const int n = n0 + c * 32;
+      if (m < g.M && n < g.N) gemm_epilogue_row32(g, m, n, r);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, BN);
+}
+
+#endif  // __CUDACC__
+
+}  // namespace magb200

@@ -1,0 +1,101 @@
+// Internal host-side declarations shared by the translation units of libmagb200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+
+namespace magb200 {
+
+struct GemmProblem {
+  const void* A = nullptr;   // K-major: [M][K] pitch lda ; MN-major: [K][M] pitch lda
+  const void* B = nullptr;   // K-major: [N][K] pitch ldb ; MN-major: [K][N] pitch ldb
+  int M = 0, N = 0, K = 0;
+  int lda = 0, ldb = 0;      // in elements
+  int a_dtype = 1, b_dtype = 1;  // DType
+  bool a_mn = false, b_mn = false;
+  int splits = 1;            // split-K (atomic epilogue only)
+  int n_split = 0;           // >0: output tiles with n0 >= n_split skip K < k_start_hi
+  int k_start_hi = 0;
+  int epi = 0;               // GemmEpilogue
+  const float* bias = nullptr;
+  void* out0 = nullptr;
+  void* out1 = nullptr;
+  const void* aux = nullptr;
+  int ldo = 0;
+  float alpha = 1.0f;
+};
+
+int gemm_launch(const GemmProblem& p, cudaStream_t stream);
+
+// ---------------------------------------------------------------- rowops.cu
+struct EmbedArgs {
+  const int64_t* ids = nullptr;      // [T]
+  const int64_t* tt = nullptr;       // [T] or null (all zero)
+  const float* visual = nullptr;     // [T][V]
+  const float* acoustic = nullptr;   // [T][A]
+  const float* word = nullptr; const float* pos = nullptr; const float* type = nullptr;
+  const float* gamma = nullptr; const float* beta = nullptr;
+  float eps = 1e-12f;
+  float p = 0.f; uint64_t seed = 0; uint32_t site = 0;
+  int V = 0, A = 0, KA = 896, T = 0, S = 0, vocab = 0, hidden = 768;
+  float* emb32 = nullptr;            // [T][768]
+  __half* amag = nullptr;            // [T][KA] or null
+};
+int embed_ln_fwd(const EmbedArgs& a, cudaStream_t st);
+int embed_ln_bwd(const EmbedArgs& a, const float* dout, float oscale, float* dword, float* dpos, float* dtype,
+                 float* dgamma, float* dbeta, cudaStream_t st);
+int mag_pack_inputs(const float* text, const float* visual, const float* acoustic, int V, int A, int KA, int T,
+                    __half* amag, cudaStream_t st);
+int mag_tail_fwd(const float* G, const float* text32, const float* gamma, const float* beta, float beta_shift, float eps,
+                 float p, uint64_t seed, uint32_t site, int T, float* out32, __half* out16, cudaStream_t st);
+int mag_tail_bwd(const float* dout, const float* G, const float* text32, const float* gamma, float beta_shift, float eps,
+                 float p, uint64_t seed, uint32_t site, int T, float oscale, __half* dG, float* dtext, float* dgamma,
+                 float* dbeta, float* dbias4, cudaStream_t st);
+int dropout_residual_ln_fwd(const float* pre, const float* res, const float* gamma, const float* beta, float eps, float p,
+                            uint64_t seed, uint32_t site, int T, float* y32, __half* y16, float* rstd, cudaStream_t st);
+int ln_bwd(const float* dy32, const float* y32, const float* gamma, const float* beta, const float* rstd, float p,
+           uint64_t seed, uint32_t site, int T, float oscale, float* dz32, __half* dpre, float* dgamma, float* dbeta,
+           float* dbias, cudaStream_t st);
+int colsum_f16(const __half* in, int T, int N, float oscale, float* out, cudaStream_t st);
+int cast_f32_f16(const float* in, __half* out, int64_t n, cudaStream_t st);
+int mag_pack_weights(const float* W_hv, const float* W_ha, const float* W_v, const float* W_a, int V, int A, int KA,
+                     __half* Bm, cudaStream_t st);
+int mag_unpack_wgrad(const float* dB, int V, int A, int KA, float* dW_hv, float* dW_ha, float* dW_v, float* dW_a,
+                     cudaStream_t st);
+int dropout_mask(uint8_t* out, int64_t n, float p, uint64_t seed, uint32_t site, cudaStream_t st);
+
+
+// ---------------------------------------------------------------- attention.cu
+int sdpa_fwd(const __half* qkv, const int64_t* mask, int B, int S, int heads, int head_dim, float p, uint64_t seed,
+             uint32_t site, __half* ctx, cudaStream_t st);
+int sdpa_bwd(const __half* qkv, const __half* dctx, const int64_t* mask, int B, int S, int heads, int head_dim, float p,
+             uint64_t seed, uint32_t site, __half* dqkv, cudaStream_t st);
+
+// ---------------------------------------------------------------- head_optim.cu
+int cls_fwd(const float* pre, const float* Wc, const float* bc, int B, int L, float p, uint64_t seed, uint32_t site,
+            float* pooled, float* logits, cudaStream_t st);
+int cls_bwd(const float* dlogits, const float* pooled, const float* Wc, int B, int L, float p, uint64_t seed,
+            uint32_t site, float oscale, __half* dpre, float* dWc, float* dbc, cudaStream_t st);
+int mse_loss(const float* logits, const float* labels, int n, float gscale, float* loss, float* dlogits, cudaStream_t st);
+int adamw_step(float* p, float* g, float* m, float* v, __half* p16, const uint8_t* decay_chunk, int64_t n, float lr,
+               float b1, float b2, float eps, float wd, int step, float gscale, int zero_grad, cudaStream_t st);
+
+}  // namespace magb200
+
+// ---------------------------------------------------------------- model_bert.cu
+struct magb200_bert_dims;
+namespace magb200 {
+size_t bert_workspace_bytes(const magb200_bert_dims& d);
+int bert_refresh_operands(const magb200_bert_dims& d, const int64_t* off, const float* params, __half* params16,
+                          cudaStream_t st);
+int bert_forward(const magb200_bert_dims& d, const int64_t* off, const float* P, const __half* P16, const int64_t* ids,
+                 const int64_t* tt, const int64_t* mask, const float* visual, const float* acoustic, void* workspace,
+                 size_t ws_bytes, float* logits, cudaStream_t st);
+int bert_backward(const magb200_bert_dims& d, const int64_t* off, const float* P, const __half* P16, const int64_t* ids,
+                  const int64_t* tt, const int64_t* mask, void* workspace, size_t ws_bytes, const float* dlogits_scaled,
+                  float* G, cudaStream_t st);
+int bert_peek(const magb200_bert_dims& d, void* workspace, int what, int layer, void* out, size_t out_bytes,
+              cudaStream_t st);
+}  // namespace magb200
+

@@ -1,0 +1,147 @@
+"""Host-side driver of the native MAG-BERT schedules (magb200_bert_forward / _backward).
+
+Owns the flat fp32 parameter buffer (the nn.Parameters are views into it), its fp16 operand mirror,
+the offsets table and the workspaces.  PyTorch is used for device memory and streams only; every
+FLOP runs in libmagb200.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import byref, c_void_p
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib as L
+from .flat import FlatLayout, bert_offsets_table, bert_param_order, packed16_numel
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise L.MagB200Error(
+            f"{what} is on {t.device}: bert_multimodal_transformer_b200 only runs on a CUDA (sm_100a) device; "
+            "there is no CPU fallback")
+
+
+class BertEngine:
+    def __init__(self, *, hidden, heads, inter, layers, vocab, max_pos, type_vocab, visual_dim, acoustic_dim,
+                 num_labels, ln_eps, beta_shift, p_hidden, p_attn, p_mag, grad_scale=1024.0):
+        if hidden != 768 or heads != 12:
+            raise NotImplementedError("libmagb200 kernels are specialised for hidden_size=768, 12 heads (bert-base)")
+        self.hidden, self.heads, self.inter, self.layers = hidden, heads, inter, layers
+        self.vocab, self.max_pos, self.type_vocab = vocab, max_pos, type_vocab
+        self.visual_dim, self.acoustic_dim, self.num_labels = visual_dim, acoustic_dim, num_labels
+        self.ln_eps, self.beta_shift = ln_eps, beta_shift
+        self.p_hidden, self.p_attn, self.p_mag = p_hidden, p_attn, p_mag
+        self.grad_scale = float(grad_scale)
+        self.ka = hidden + 128
+        self.order = bert_param_order(layers)
+        self.layout: Optional[FlatLayout] = None
+        self.flat: Optional[torch.Tensor] = None       # fp32 master parameters
+        self.flat16: Optional[torch.Tensor] = None     # fp16 mirror + packed MAG gate matrix
+        self.offsets = None
+        self.operands_dirty = True
+        self._eval_ws: Dict[tuple, torch.Tensor] = {}
+        self._expected_ptrs = None
+
+    # ------------------------------------------------------------------ parameters
+    def bind(self, named_params: Dict[str, torch.nn.Parameter]):
+        """(Re)build the flat buffer on the parameters' device and make every parameter a view of it."""
+        missing = [n for n in self.order if n not in named_params]
+        if missing:
+            raise KeyError(f"parameters missing from the model: {missing[:4]}...")
+        dev = named_params[self.order[0]].device
+        _require_cuda(named_params[self.order[0]], "model parameters")
+        if self.layout is None:
+            self.layout = FlatLayout([(n, tuple(named_params[n].shape)) for n in self.order])
+            self.offsets = bert_offsets_table(self.layout, self.layers, self.hidden, self.ka)
+        flat = torch.zeros(self.layout.total, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for n in self.order:
+                p = named_params[n]
+                v = self.layout.view(flat, n)
+                v.copy_(p.detach().to(device=dev, dtype=torch.float32))
+                p.data = v
+        self.flat = flat
+        self.flat16 = torch.zeros(self.layout.total + packed16_numel(self.hidden, self.ka), dtype=torch.float16,
+                                  device=dev)
+        self._expected_ptrs = [(named_params[n], self.layout.view(flat, n).data_ptr()) for n in self.order]
+        self.operands_dirty = True
+        self._eval_ws.clear()
+
+    def is_bound(self) -> bool:
+        if self.flat is None:
+            return False
+        for p, ptr in self._expected_ptrs:
+            if p.data_ptr() != ptr:
+                return False
+        return True
+
+    def dims(self, batch, seq, training, seed=0) -> L.BertDims:
+        d = L.BertDims()
+        d.batch, d.seq, d.hidden, d.heads, d.inter, d.layers = batch, seq, self.hidden, self.heads, self.inter, self.layers
+        d.vocab, d.max_pos, d.type_vocab = self.vocab, self.max_pos, self.type_vocab
+        d.visual_dim, d.acoustic_dim, d.num_labels, d.ka = self.visual_dim, self.acoustic_dim, self.num_labels, self.ka
+        d.ln_eps, d.mag_ln_eps, d.beta_shift = self.ln_eps, 1e-5, self.beta_shift
+        if training:
+            d.p_hidden, d.p_attn, d.p_mag, d.p_cls = self.p_hidden, self.p_attn, self.p_mag, self.p_hidden
+        else:
+            d.p_hidden = d.p_attn = d.p_mag = d.p_cls = 0.0
+        d.grad_scale = self.grad_scale
+        d.seed = seed
+        return d
+
+    def refresh_operands(self, dims=None):
+        lib = L.load()
+        d = dims or self.dims(1, 1, False)
+        L.check(lib.magb200_bert_refresh_operands(byref(d), self.offsets, L.ptr(self.flat), L.ptr(self.flat16),
+                                                  L.current_stream()))
+        self.operands_dirty = False
+
+    def workspace(self, dims, keep: bool) -> torch.Tensor:
+        lib = L.load()
+        nbytes = lib.magb200_bert_workspace_bytes(byref(dims))
+        if keep:   # saved for backward: a fresh buffer per autograd graph
+            return torch.empty(nbytes, dtype=torch.uint8, device=self.flat.device)
+        key = (dims.batch, dims.seq)
+        ws = self._eval_ws.get(key)
+        if ws is None or ws.numel() < nbytes:
+            self._eval_ws.clear()
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=self.flat.device)
+            self._eval_ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------ schedules
+    def forward(self, dims, ws, input_ids, token_type_ids, attention_mask, visual, acoustic, logits):
+        lib = L.load()
+        L.check(lib.magb200_bert_forward(byref(dims), self.offsets, L.ptr(self.flat), L.ptr(self.flat16),
+                                         L.ptr(input_ids), L.ptr(token_type_ids), L.ptr(attention_mask),
+                                         L.ptr(visual), L.ptr(acoustic), L.ptr(ws), ws.numel(), L.ptr(logits),
+                                         L.current_stream()))
+
+    def backward(self, dims, ws, input_ids, token_type_ids, attention_mask, dlogits_scaled, grads):
+        lib = L.load()
+        L.check(lib.magb200_bert_backward(byref(dims), self.offsets, L.ptr(self.flat), L.ptr(self.flat16),
+                                          L.ptr(input_ids), L.ptr(token_type_ids), L.ptr(attention_mask), L.ptr(ws),
+                                          ws.numel(), L.ptr(dlogits_scaled), L.ptr(grads), L.current_stream()))
+
+    def peek(self, dims, ws, what, layer=0):
+        lib = L.load()
+        T = dims.batch * dims.seq
+        shape = {L.PEEK_EMB: (dims.batch, dims.seq, self.hidden), L.PEEK_MAG: (dims.batch, dims.seq, self.hidden),
+                 L.PEEK_LAYER_OUT: (dims.batch, dims.seq, self.hidden), L.PEEK_POOLED: (dims.batch, self.hidden),
+                 L.PEEK_GATES: (T, 4 * self.hidden)}[what]
+        out = torch.empty(shape, dtype=torch.float32, device=self.flat.device)
+        L.check(lib.magb200_bert_peek(byref(dims), L.ptr(ws), what, layer, L.ptr(out), out.numel() * 4,
+                                      L.current_stream()))
+        return out
+
+
+def prep_inputs(device, input_ids, visual, acoustic, attention_mask, token_type_ids):
+    """Contiguous device tensors of the dtypes the C ABI expects."""
+    ids = input_ids.to(device=device, dtype=torch.int64).contiguous()
+    vis = visual.to(device=device, dtype=torch.float32).contiguous()
+    aco = acoustic.to(device=device, dtype=torch.float32).contiguous()
+    mask = None if attention_mask is None else attention_mask.to(device=device, dtype=torch.int64).contiguous()
+    tt = None if token_type_ids is None else token_type_ids.to(device=device, dtype=torch.int64).contiguous()
+    return ids, vis, aco, mask, tt

@@ -1,0 +1,197 @@
+/* libmagb200 -- C ABI of the B200-native MAG-BERT / MAG-XLNet hot path.
+ *
+ * The reference (WasifurRahman/BERT_multimodal_transformer) has no FFI of its own: its hot path
+ * is Python calling torch ops.  This header is the boundary a maintainer would bind from the
+ * reference's modules (ctypes stub in INTEGRATION.md); each entry point cites the reference
+ * lines whose arithmetic it replaces.
+ *
+ * Conventions: every pointer is a DEVICE pointer owned by the caller (16-byte aligned, row-major,
+ * contiguous unless a pitch is given); nothing is allocated or freed by the library; work is
+ * enqueued on `stream` (a cudaStream_t) and the call returns without synchronising.  Return
+ * value 0 = success, otherwise a cudaError_t-style code or -1 for argument errors, with the
+ * message available from magb200_last_error() (thread-local).
+ */
+#ifndef MAGB200_H_
+#define MAGB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAGB200_VERSION 100
+
+/* element types */
+#define MAGB200_F32 0  /* fp32 in memory; GEMM operands are read as tf32 */
+#define MAGB200_F16 1
+#define MAGB200_BF16 2
+
+/* GEMM epilogues: v = alpha * acc + bias[n] */
+#define MAGB200_EPI_STORE_F32 0      /* out0(f32) = v (+ aux(f32) when aux != NULL) */
+#define MAGB200_EPI_STORE_F16 1      /* out0(f16) = v */
+#define MAGB200_EPI_STORE_BF16 2     /* out0(bf16) = v */
+#define MAGB200_EPI_GELU_F16 3       /* out0(f16) = gelu_erf(v); out1(f16) = v when out1 != NULL */
+#define MAGB200_EPI_DGELU_F16 4      /* out0(f16) = v * gelu_erf'(aux(f16)) */
+#define MAGB200_EPI_ATOMIC_F32 5     /* out0(f32) += v */
+#define MAGB200_EPI_STORE_F32_F16 6  /* out0(f32) = v; out1(f16) = v */
+#define MAGB200_EPI_RELU_F32 7       /* out0(f32) = max(v, 0) */
+
+const char* magb200_last_error(void);
+int magb200_version(void);
+/* 0 iff the current device is an sm_100 part */
+int magb200_device_check(void);
+
+/* D[M,N] = A[M,K] * B[N,K]^T on tcgen05 tensor cores (TMA-fed, TMEM accumulators).
+ * Replaces every nn.Linear / einsum contraction on the reference path (F.linear at
+ * modeling.py:27-30; BertSelfAttention/BertSelfOutput/BertIntermediate/BertOutput Linears
+ * called through bert.py:221-229; einsum projections called through xlnet.py:374-385) and
+ * their autograd dgrad/wgrad counterparts (multimodal_driver.py:378).
+ *   a_mn_major = 0: A stored [M][K] (pitch lda);  1: A stored [K][M] (pitch lda)
+ *   b_mn_major = 0: B stored [N][K] (pitch ldb);  1: B stored [K][N] (pitch ldb)
+ *   splits > 1 (ATOMIC epilogue only): split-K over blockIdx.z
+ *   n_split > 0: output columns >= n_split only accumulate K >= k_start_hi (block-sparse B). */
+int magb200_gemm(const void* A, const void* B, int M, int N, int K, int lda, int ldb, int a_dtype, int b_dtype,
+                 int a_mn_major, int b_mn_major, int epilogue, const float* bias, void* out0, void* out1,
+                 const void* aux, int ldo, float alpha, int splits, int n_split, int k_start_hi, void* stream);
+
+
+/* ------------------------------------------------------------------------------------------------
+ * Row-wise operators (fp32 activations, hidden size 768).  Dropout uses a counter-based RNG:
+ * the keep-mask of a site is a pure function of (seed, site, element index), so backward
+ * regenerates it.  p = 0 disables dropout (eval mode). */
+
+/* keep-mask bytes (1 = keep) the kernels use for (seed, site) over n elements -- test hook */
+int magb200_dropout_mask(uint8_t* out, int64_t n, float p, uint64_t seed, uint32_t site, void* stream);
+
+/* fp32 -> fp16 copy (GEMM operand refresh) */
+int magb200_cast_f32_f16(const float* in, void* out_f16, int64_t n, void* stream);
+
+/* BertEmbeddings.forward (transformers 3.0.2, called at bert.py:211-216):
+ *   emb32[t] = dropout(LayerNorm(word[ids[t]] + pos[t % S] + type[tt[t]]))
+ * and, when amag16 != NULL, the packed MAG GEMM operand row
+ *   amag16[t] = [ fp16(emb32[t]) | fp16(visual[t]) | fp16(acoustic[t]) | 0.. ]   (pitch ka = 896) */
+int magb200_embed_ln_fwd(const int64_t* ids, const int64_t* token_type_ids, const float* visual, const float* acoustic,
+                         const float* word, const float* pos, const float* type, const float* gamma, const float* beta,
+                         float eps, float p, uint64_t seed, uint32_t site, int V, int A, int ka, int T, int S, int vocab,
+                         float* emb32, void* amag16, void* stream);
+int magb200_embed_ln_bwd(const float* dout, const int64_t* ids, const int64_t* token_type_ids, const float* word,
+                         const float* pos, const float* type, const float* gamma, float eps, float p, uint64_t seed,
+                         uint32_t site, int T, int S, int vocab, float out_scale, float* dword, float* dpos, float* dtype,
+                         float* dgamma, float* dbeta, void* stream);
+
+/* MAG.forward (modeling.py:25-51), all of it:
+ *   gates GEMM on tcgen05 (the four Linears W_hv, W_ha, W_v, W_a as one block matrix) followed by the
+ *   fused tail (ReLU gates, h_m, the two L2 norms, alpha = min(beta*|text|/(|h_m|+1e-6), 1) with the
+ *   hm_norm == 0 guard, shift, LayerNorm(eps), dropout).
+ * text32 [T][768], visual [T][V], acoustic [T][A]; packed16 = magb200_mag_pack_weights output;
+ * bias4 = [b_hv | b_ha | b_v | b_a]; scratch: amag16 [T][ka] fp16, gates32 [T][3072] fp32.
+ * out32 [T][768]; out16 optional fp16 copy. */
+int magb200_mag_pack_weights(const float* W_hv, const float* W_ha, const float* W_v, const float* W_a, int V, int A,
+                             int ka, void* packed16, void* stream);
+int magb200_mag_fwd(const float* text32, const float* visual, const float* acoustic, const void* packed16,
+                    const float* bias4, const float* ln_gamma, const float* ln_beta, float beta_shift, float ln_eps,
+                    float p, uint64_t seed, uint32_t site, int V, int A, int ka, int T, void* amag16, float* gates32,
+                    float* out32, void* out16, void* stream);
+/* Backward of magb200_mag_fwd from saved amag16 / gates32.  dout is the (loss-scaled) gradient of out32.
+ * Writes dtext32 [T][768] (still scaled); accumulates (+=) out_scale * {dW_hv, dW_ha, dW_v, dW_a, dbias4, dgamma, dbeta}.
+ * scratch: dgates16 [T][3072] fp16, dpacked32 [3072][ka] fp32. */
+int magb200_mag_bwd(const float* dout, const float* text32, const void* amag16, const float* gates32,
+                    const void* packed16, const float* ln_gamma, float beta_shift, float ln_eps, float p, uint64_t seed,
+                    uint32_t site, int V, int A, int ka, int T, float out_scale, void* dgates16, float* dpacked32,
+                    float* dtext32, float* dW_hv, float* dW_ha, float* dW_v, float* dW_a, float* dbias4, float* dgamma,
+                    float* dbeta, void* stream);
+
+/* BertSelfOutput / BertOutput tail (transformers 3.0.2, inside bert.py:221-229):
+ *   y = LayerNorm(dropout(pre) + res);  y16 optional fp16 copy; rstd optional [T] (needed by backward) */
+int magb200_dropout_residual_ln_fwd(const float* pre, const float* res, const float* gamma, const float* beta,
+                                    float eps, float p, uint64_t seed, uint32_t site, int T, float* y32, void* y16,
+                                    float* rstd, void* stream);
+/* dz32 = gradient wrt (dropout(pre)+res); dpre16 = fp16 dropout-masked gradient wrt pre; dgamma/dbeta/dbias += */
+int magb200_ln_bwd(const float* dy32, const float* y32, const float* gamma, const float* beta, const float* rstd,
+                   float p, uint64_t seed, uint32_t site, int T, float out_scale, float* dz32, void* dpre16,
+                   float* dgamma, float* dbeta, float* dbias, void* stream);
+/* out[n] += sum_t in[t][n], fp16 input */
+int magb200_colsum_f16(const void* in_f16, int T, int N, float out_scale, float* out, void* stream);
+
+/* BertSelfAttention core (transformers 3.0.2, inside bert.py:221-229):
+ *   ctx = dropout(softmax(q k^T / 8 + (1 - mask) * -10000)) v  per (batch, head)
+ * qkv16 [B*S][3*heads*64] fp16 (q | k | v), mask [B][S] int64 (1 = attend) or NULL, ctx16 [B*S][heads*64] */
+int magb200_sdpa_fwd(const void* qkv16, const int64_t* mask, int B, int S, int heads, int head_dim, float p,
+                     uint64_t seed, uint32_t site, void* ctx16, void* stream);
+int magb200_sdpa_bwd(const void* qkv16, const void* dctx16, const int64_t* mask, int B, int S, int heads, int head_dim,
+                     float p, uint64_t seed, uint32_t site, void* dqkv16, void* stream);
+
+/* BertPooler tanh + dropout + classifier (bert.py:231, 304-307): pre [B][768] = pooler dense output */
+int magb200_cls_fwd(const float* pre, const float* Wc, const float* bc, int B, int num_labels, float p, uint64_t seed,
+                    uint32_t site, float* pooled, float* logits, void* stream);
+int magb200_cls_bwd(const float* dlogits, const float* pooled, const float* Wc, int B, int num_labels, float p,
+                    uint64_t seed, uint32_t site, float out_scale, void* dpre16, float* dWc, float* dbc, void* stream);
+/* MSELoss()(logits.view(-1), labels.view(-1)) (multimodal_driver.py:371-373; bert.py:313-317):
+ * loss[0] = mean((logits-labels)^2); dlogits (optional) = 2 (logits-labels) / n * grad_scale */
+int magb200_mse_loss(const float* logits, const float* labels, int n, float grad_scale, float* loss, float* dlogits,
+                     void* stream);
+/* transformers 3.0.2 AdamW.step (multimodal_driver.py:345-350, 383) over a flat buffer of n (multiple of 256)
+ * parameters: grads are multiplied by grad_unscale first; decay_chunk[i] != 0 applies weight decay to elements
+ * [256 i, 256 i + 256).  Optionally zeroes the gradient and refreshes the fp16 copy p16 in the same pass. */
+int magb200_adamw_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* p16,
+                       const uint8_t* decay_chunk, int64_t n, float lr, float beta1, float beta2, float eps,
+                       float weight_decay, int step, float grad_unscale, int zero_grad, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Whole-model schedules: MAG_BertForSequenceClassification.forward (bert.py:251-324) and the autograd
+ * pass of multimodal_driver.py:378, as one enqueue each.
+ *
+ * Parameters live in ONE flat fp32 buffer `params` (fp16 mirror `params16` at the same element
+ * offsets, gradients `grads` likewise); `off` is a host array of element offsets indexed by the
+ * MAGB200_OFF_* constants, every tensor starting on a 256-element boundary.  Required adjacency:
+ * query|key|value weights contiguous ([3H][H]) and their biases contiguous; b_hv|b_ha|b_v|b_a
+ * contiguous.  params16 additionally holds the packed MAG gate matrix at off[MAGB200_OFF_MAG_PACKED16]. */
+#define MAGB200_MAX_LAYERS 48
+enum {
+  MAGB200_OFF_WORD = 0, MAGB200_OFF_POS, MAGB200_OFF_TYPE, MAGB200_OFF_EMB_LN_W, MAGB200_OFF_EMB_LN_B,
+  MAGB200_OFF_MAG_WHV, MAGB200_OFF_MAG_WHA, MAGB200_OFF_MAG_WV, MAGB200_OFF_MAG_WA, MAGB200_OFF_MAG_BIAS4,
+  MAGB200_OFF_MAG_LN_W, MAGB200_OFF_MAG_LN_B, MAGB200_OFF_POOL_W, MAGB200_OFF_POOL_B, MAGB200_OFF_CLS_W,
+  MAGB200_OFF_CLS_B, MAGB200_OFF_MAG_PACKED16, MAGB200_OFF_TOTAL, MAGB200_OFF_RESERVED0, MAGB200_OFF_RESERVED1,
+  MAGB200_OFF_LAYER0 = 20
+};
+enum {
+  MAGB200_LOFF_QKV_W = 0, MAGB200_LOFF_QKV_B, MAGB200_LOFF_AO_W, MAGB200_LOFF_AO_B, MAGB200_LOFF_LN1_W,
+  MAGB200_LOFF_LN1_B, MAGB200_LOFF_F1_W, MAGB200_LOFF_F1_B, MAGB200_LOFF_F2_W, MAGB200_LOFF_F2_B,
+  MAGB200_LOFF_LN2_W, MAGB200_LOFF_LN2_B, MAGB200_OFF_PER_LAYER = 12
+};
+enum { MAGB200_PEEK_EMB = 0, MAGB200_PEEK_MAG, MAGB200_PEEK_LAYER_OUT, MAGB200_PEEK_POOLED, MAGB200_PEEK_GATES };
+
+typedef struct magb200_bert_dims {
+  int32_t batch, seq, hidden, heads, inter, layers, vocab, max_pos, type_vocab;
+  int32_t visual_dim, acoustic_dim, num_labels, ka;   /* ka = hidden + 128: padded K of the MAG gate GEMM */
+  float ln_eps, mag_ln_eps, beta_shift;
+  float p_hidden, p_attn, p_mag, p_cls;               /* dropout probabilities (0 = eval) */
+  float grad_scale;                                    /* loss scale carried by every gradient in backward */
+  uint64_t seed;                                       /* dropout seed of this step */
+} magb200_bert_dims;
+
+size_t magb200_bert_workspace_bytes(const magb200_bert_dims* dims);
+/* params -> params16 (cast) + packed MAG gate matrix; call after the master weights change */
+int magb200_bert_refresh_operands(const magb200_bert_dims* dims, const int64_t* off, const float* params,
+                                  void* params16, void* stream);
+int magb200_bert_forward(const magb200_bert_dims* dims, const int64_t* off, const float* params, const void* params16,
+                         const int64_t* input_ids, const int64_t* token_type_ids, const int64_t* attention_mask,
+                         const float* visual, const float* acoustic, void* workspace, size_t workspace_bytes,
+                         float* logits, void* stream);
+/* dlogits_scaled = dL/dlogits * dims->grad_scale (activation gradients are loss-scaled fp16 inside);
+ * grads (+=) receive dL/dparam, unscaled.  Backward kernels that write parameter gradients take
+ * out_scale (= 1/grad_scale) for the same reason. */
+int magb200_bert_backward(const magb200_bert_dims* dims, const int64_t* off, const float* params, const void* params16,
+                          const int64_t* input_ids, const int64_t* token_type_ids, const int64_t* attention_mask,
+                          void* workspace, size_t workspace_bytes, const float* dlogits_scaled, float* grads,
+                          void* stream);
+/* copy a saved activation out of the workspace (tests): MAGB200_PEEK_* */
+int magb200_bert_peek(const magb200_bert_dims* dims, void* workspace, int what, int layer, void* out, size_t out_bytes,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAGB200_H_ */
