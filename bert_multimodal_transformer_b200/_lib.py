@@ -34,7 +34,7 @@ class BertDims(Structure):
     _fields_ = [(n, c_int32) for n in ("batch", "seq", "hidden", "heads", "inter", "layers", "vocab", "max_pos",
                                        "type_vocab", "visual_dim", "acoustic_dim", "num_labels", "ka")] + \
                [(n, c_float) for n in ("ln_eps", "mag_ln_eps", "beta_shift", "p_hidden", "p_attn", "p_mag", "p_cls",
-                                       "grad_scale")] + [("seed", c_uint64)]
+                                       "grad_scale")] + [("seed", c_uint64), ("seed_dev", c_void_p)]
 
 
 _lib = None
@@ -43,6 +43,7 @@ _lib = None
 SIGNATURES = {
     "magb200_last_error": (c_char_p, []),
     "magb200_version": (c_int, []),
+    "magb200_launch_count": (c_uint64, []),
     "magb200_device_check": (c_int, []),
     "magb200_gemm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                              c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_int, c_int, c_int,
@@ -72,7 +73,7 @@ SIGNATURES = {
                                 c_void_p, c_void_p, c_void_p, c_void_p]),
     "magb200_mse_loss": (c_int, [c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "magb200_adamw_step": (c_int, [c_void_p] * 6 + [c_int64, c_float, c_float, c_float, c_float, c_float, c_int,
-                                                    c_float, c_int, c_void_p]),
+                                                    c_float, c_int, c_void_p, c_void_p]),
     "magb200_bert_workspace_bytes": (c_size_t, [POINTER(BertDims)]),
     "magb200_bert_refresh_operands": (c_int, [POINTER(BertDims), POINTER(c_int64), c_void_p, c_void_p, c_void_p]),
     "magb200_bert_forward": (c_int, [POINTER(BertDims), POINTER(c_int64)] + [c_void_p] * 8 + [c_size_t, c_void_p,

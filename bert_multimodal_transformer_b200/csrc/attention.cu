@@ -63,8 +63,9 @@ __device__ __forceinline__ bool keep_prob(uint64_t seed, uint32_t site, uint64_t
 template <int MAXJ>  // keys per lane = ceil(S / 32) <= MAXJ
 __global__ void __launch_bounds__(AW * 32) sdpa_fwd_kernel(const __half* __restrict__ qkv,
                                                            const int64_t* __restrict__ mask, int S, int heads,
-                                                           float scale, uint32_t thresh, float dscale, uint64_t seed,
+                                                           float scale, uint32_t thresh, float dscale, Seed seed_in,
                                                            uint32_t site, __half* __restrict__ ctx) {
+  const uint64_t seed = seed_in.ptr ? *seed_in.ptr : seed_in.value;
   extern __shared__ uint8_t smem_att[];
   __half* sK = reinterpret_cast<__half*>(smem_att);
   __half* sV = sK + S * KP;
@@ -132,8 +133,9 @@ template <int MAXJ>
 __global__ void __launch_bounds__(AW * 32) sdpa_bwd_kernel(const __half* __restrict__ qkv,
                                                            const __half* __restrict__ dctx,
                                                            const int64_t* __restrict__ mask, int S, int heads,
-                                                           float scale, uint32_t thresh, float dscale, uint64_t seed,
+                                                           float scale, uint32_t thresh, float dscale, Seed seed_in,
                                                            uint32_t site, __half* __restrict__ dqkv) {
+  const uint64_t seed = seed_in.ptr ? *seed_in.ptr : seed_in.value;
   extern __shared__ uint8_t smem_att[];
   __half* sK = reinterpret_cast<__half*>(smem_att);
   __half* sV = sK + S * KP;
@@ -237,7 +239,7 @@ static inline void drop_params(float p, uint32_t& thresh, float& scale) {
 }
 
 template <int MAXJ>
-static int launch_fwd(const __half* qkv, const int64_t* mask, int B, int S, int heads, float p, uint64_t seed,
+static int launch_fwd(const __half* qkv, const int64_t* mask, int B, int S, int heads, float p, Seed seed,
                       uint32_t site, __half* ctx, cudaStream_t st) {
   uint32_t th; float ds;
   drop_params(p, th, ds);
@@ -250,10 +252,11 @@ static int launch_fwd(const __half* qkv, const int64_t* mask, int B, int S, int 
   }
   k<<<dim3(heads, B), AW * 32, smem, st>>>(qkv, mask, S, heads, 0.125f, th, ds, seed, site, ctx);
   MAGB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
-int sdpa_fwd(const __half* qkv, const int64_t* mask, int B, int S, int heads, int head_dim, float p, uint64_t seed,
+int sdpa_fwd(const __half* qkv, const int64_t* mask, int B, int S, int heads, int head_dim, float p, Seed seed,
              uint32_t site, __half* ctx, cudaStream_t st) {
   MAGB_REQUIRE(head_dim == DH, "sdpa: head_dim must be 64");
   MAGB_REQUIRE(S >= 1 && S <= 512, "sdpa: sequence length %d out of range [1,512]", S);
@@ -265,7 +268,7 @@ int sdpa_fwd(const __half* qkv, const int64_t* mask, int B, int S, int heads, in
 
 template <int MAXJ>
 static int launch_bwd(const __half* qkv, const __half* dctx, const int64_t* mask, int B, int S, int heads, float p,
-                      uint64_t seed, uint32_t site, __half* dqkv, cudaStream_t st) {
+                      Seed seed, uint32_t site, __half* dqkv, cudaStream_t st) {
   uint32_t th; float ds;
   drop_params(p, th, ds);
   const size_t smem = (size_t)3 * S * KP * sizeof(__half) + (size_t)S * (DH + 1) * sizeof(float) +
@@ -278,11 +281,12 @@ static int launch_bwd(const __half* qkv, const __half* dctx, const int64_t* mask
   }
   k<<<dim3(heads, B), AW * 32, smem, st>>>(qkv, dctx, mask, S, heads, 0.125f, th, ds, seed, site, dqkv);
   MAGB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
 int sdpa_bwd(const __half* qkv, const __half* dctx, const int64_t* mask, int B, int S, int heads, int head_dim,
-             float p, uint64_t seed, uint32_t site, __half* dqkv, cudaStream_t st) {
+             float p, Seed seed, uint32_t site, __half* dqkv, cudaStream_t st) {
   MAGB_REQUIRE(head_dim == DH, "sdpa: head_dim must be 64");
   MAGB_REQUIRE(S >= 1 && S <= 128, "sdpa backward: sequence length %d out of range [1,128] (materialises S x S)", S);
   if (S <= 64) return launch_bwd<2>(qkv, dctx, mask, B, S, heads, p, seed, site, dqkv, st);

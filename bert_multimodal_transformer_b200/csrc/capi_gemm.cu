@@ -15,6 +15,8 @@ void set_last_error(const char* fmt, ...) {
   vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
   va_end(ap);
 }
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
 }  // namespace magb200
 
 using namespace magb200;
@@ -24,6 +26,8 @@ extern "C" {
 const char* magb200_last_error(void) { return g_last_error; }
 
 int magb200_version(void) { return MAGB200_VERSION; }
+
+unsigned long long magb200_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 int magb200_device_check(void) {
   int dev = 0;

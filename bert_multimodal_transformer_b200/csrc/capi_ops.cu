@@ -16,7 +16,7 @@ using namespace magb200;
 extern "C" {
 
 int magb200_dropout_mask(uint8_t* out, int64_t n, float p, uint64_t seed, uint32_t site, void* stream) {
-  return dropout_mask(out, n, p, seed, site, ST);
+  return dropout_mask(out, n, p, Seed{seed, nullptr}, site, ST);
 }
 
 int magb200_cast_f32_f16(const float* in, void* out_f16, int64_t n, void* stream) {
@@ -29,7 +29,7 @@ int magb200_embed_ln_fwd(const int64_t* ids, const int64_t* token_type_ids, cons
                          float* emb32, void* amag16, void* stream) {
   EmbedArgs e;
   e.ids = ids; e.tt = token_type_ids; e.visual = visual; e.acoustic = acoustic; e.word = word; e.pos = pos;
-  e.type = type; e.gamma = gamma; e.beta = beta; e.eps = eps; e.p = p; e.seed = seed; e.site = site; e.V = V; e.A = A;
+  e.type = type; e.gamma = gamma; e.beta = beta; e.eps = eps; e.p = p; e.seed = Seed{seed, nullptr}; e.site = site; e.V = V; e.A = A;
   e.KA = ka; e.T = T; e.S = S; e.vocab = vocab; e.emb32 = emb32; e.amag = reinterpret_cast<__half*>(amag16);
   return embed_ln_fwd(e, ST);
 }
@@ -40,7 +40,7 @@ int magb200_embed_ln_bwd(const float* dout, const int64_t* ids, const int64_t* t
                          float* dgamma, float* dbeta, void* stream) {
   EmbedArgs e;
   e.ids = ids; e.tt = token_type_ids; e.word = word; e.pos = pos; e.type = type; e.gamma = gamma; e.eps = eps; e.p = p;
-  e.seed = seed; e.site = site; e.T = T; e.S = S; e.vocab = vocab;
+  e.seed = Seed{seed, nullptr}; e.site = site; e.T = T; e.S = S; e.vocab = vocab;
   return embed_ln_bwd(e, dout, out_scale, dword, dpos, dtype, dgamma, dbeta, ST);
 }
 
@@ -61,7 +61,7 @@ int magb200_mag_fwd(const float* text32, const float* visual, const float* acous
   g.a_dtype = DT_F16; g.b_dtype = DT_F16; g.epi = EPI_STORE_F32; g.bias = bias4; g.out0 = gates32; g.ldo = 4 * H;
   g.n_split = 2 * H; g.k_start_hi = H;
   RUN(gemm_launch(g, ST));
-  return mag_tail_fwd(gates32, text32, ln_gamma, ln_beta, beta_shift, ln_eps, p, seed, site, T, out32,
+  return mag_tail_fwd(gates32, text32, ln_gamma, ln_beta, beta_shift, ln_eps, p, Seed{seed, nullptr}, site, T, out32,
                       reinterpret_cast<__half*>(out16), ST);
 }
 
@@ -72,7 +72,7 @@ int magb200_mag_bwd(const float* dout, const float* text32, const void* amag16, 
                     void* stream) {
   const int H = 768;
   MAGB_REQUIRE(ka == H + 128, "mag: ka must be 896");
-  RUN(mag_tail_bwd(dout, gates32, text32, ln_gamma, beta_shift, ln_eps, p, seed, site, T, out_scale,
+  RUN(mag_tail_bwd(dout, gates32, text32, ln_gamma, beta_shift, ln_eps, p, Seed{seed, nullptr}, site, T, out_scale,
                    reinterpret_cast<__half*>(dgates16), dtext32, dgamma, dbeta, dbias4, ST));
   MAGB_CHECK_CUDA(cudaMemsetAsync(dpacked32, 0, (size_t)4 * H * ka * sizeof(float), ST));
   GemmProblem w;  // dB[4H][ka] += dG^T * Amag
@@ -89,14 +89,14 @@ int magb200_mag_bwd(const float* dout, const float* text32, const void* amag16, 
 int magb200_dropout_residual_ln_fwd(const float* pre, const float* res, const float* gamma, const float* beta,
                                     float eps, float p, uint64_t seed, uint32_t site, int T, float* y32, void* y16,
                                     float* rstd, void* stream) {
-  return dropout_residual_ln_fwd(pre, res, gamma, beta, eps, p, seed, site, T, y32, reinterpret_cast<__half*>(y16), rstd,
+  return dropout_residual_ln_fwd(pre, res, gamma, beta, eps, p, Seed{seed, nullptr}, site, T, y32, reinterpret_cast<__half*>(y16), rstd,
                                  ST);
 }
 
 int magb200_ln_bwd(const float* dy32, const float* y32, const float* gamma, const float* beta, const float* rstd,
                    float p, uint64_t seed, uint32_t site, int T, float out_scale, float* dz32, void* dpre16,
                    float* dgamma, float* dbeta, float* dbias, void* stream) {
-  return ln_bwd(dy32, y32, gamma, beta, rstd, p, seed, site, T, out_scale, dz32, reinterpret_cast<__half*>(dpre16), dgamma, dbeta,
+  return ln_bwd(dy32, y32, gamma, beta, rstd, p, Seed{seed, nullptr}, site, T, out_scale, dz32, reinterpret_cast<__half*>(dpre16), dgamma, dbeta,
                 dbias, ST);
 }
 
@@ -106,24 +106,24 @@ int magb200_colsum_f16(const void* in_f16, int T, int N, float out_scale, float*
 
 int magb200_sdpa_fwd(const void* qkv16, const int64_t* mask, int B, int S, int heads, int head_dim, float p,
                      uint64_t seed, uint32_t site, void* ctx16, void* stream) {
-  return sdpa_fwd(reinterpret_cast<const __half*>(qkv16), mask, B, S, heads, head_dim, p, seed, site,
+  return sdpa_fwd(reinterpret_cast<const __half*>(qkv16), mask, B, S, heads, head_dim, p, Seed{seed, nullptr}, site,
                   reinterpret_cast<__half*>(ctx16), ST);
 }
 
 int magb200_sdpa_bwd(const void* qkv16, const void* dctx16, const int64_t* mask, int B, int S, int heads, int head_dim,
                      float p, uint64_t seed, uint32_t site, void* dqkv16, void* stream) {
   return sdpa_bwd(reinterpret_cast<const __half*>(qkv16), reinterpret_cast<const __half*>(dctx16), mask, B, S, heads,
-                  head_dim, p, seed, site, reinterpret_cast<__half*>(dqkv16), ST);
+                  head_dim, p, Seed{seed, nullptr}, site, reinterpret_cast<__half*>(dqkv16), ST);
 }
 
 int magb200_cls_fwd(const float* pre, const float* Wc, const float* bc, int B, int num_labels, float p, uint64_t seed,
                     uint32_t site, float* pooled, float* logits, void* stream) {
-  return cls_fwd(pre, Wc, bc, B, num_labels, p, seed, site, pooled, logits, ST);
+  return cls_fwd(pre, Wc, bc, B, num_labels, p, Seed{seed, nullptr}, site, pooled, logits, ST);
 }
 
 int magb200_cls_bwd(const float* dlogits, const float* pooled, const float* Wc, int B, int num_labels, float p,
                     uint64_t seed, uint32_t site, float out_scale, void* dpre16, float* dWc, float* dbc, void* stream) {
-  return cls_bwd(dlogits, pooled, Wc, B, num_labels, p, seed, site, out_scale, reinterpret_cast<__half*>(dpre16), dWc, dbc, ST);
+  return cls_bwd(dlogits, pooled, Wc, B, num_labels, p, Seed{seed, nullptr}, site, out_scale, reinterpret_cast<__half*>(dpre16), dWc, dbc, ST);
 }
 
 int magb200_mse_loss(const float* logits, const float* labels, int n, float grad_scale, float* loss, float* dlogits,
@@ -133,9 +133,10 @@ int magb200_mse_loss(const float* logits, const float* labels, int n, float grad
 
 int magb200_adamw_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* p16,
                        const uint8_t* decay_chunk, int64_t n, float lr, float beta1, float beta2, float eps,
-                       float weight_decay, int step, float grad_unscale, int zero_grad, void* stream) {
+                       float weight_decay, int step, float grad_unscale, int zero_grad, const float* hyper_dev,
+                       void* stream) {
   return adamw_step(params, grads, exp_avg, exp_avg_sq, reinterpret_cast<__half*>(p16), decay_chunk, n, lr, beta1, beta2,
-                    eps, weight_decay, step, grad_unscale, zero_grad, ST);
+                    eps, weight_decay, step, grad_unscale, zero_grad, hyper_dev, ST);
 }
 
 size_t magb200_bert_workspace_bytes(const magb200_bert_dims* dims) { return bert_workspace_bytes(*dims); }

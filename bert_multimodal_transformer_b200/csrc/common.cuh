@@ -18,6 +18,7 @@ namespace magb200 {
 // ----------------------------------------------------------------------------------------
 // error plumbing (host)
 void set_last_error(const char* fmt, ...);
+void count_launch();   // every kernel launch of the library bumps a process-wide counter (magb200_launch_count)
 #define MAGB_CHECK_CUDA(expr)                                                                   \
   do {                                                                                          \
     cudaError_t _e = (expr);                                                                    \

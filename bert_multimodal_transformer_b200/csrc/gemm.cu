@@ -97,6 +97,7 @@ static int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const Ge
   }
   kern<<<grid, 192, SM::TOTAL, st>>>(ta, tb, g);
   MAGB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 

@@ -11,8 +11,9 @@ constexpr int H = 768;
 // pooled = tanh(pre)  [saved, fp32] ; logits = dropout(pooled) . Wc^T + bc        one warp per batch row
 __global__ void __launch_bounds__(128) cls_fwd_kernel(const float* __restrict__ pre, const float* __restrict__ Wc,
                                                       const float* __restrict__ bc, int B, int L, uint32_t thresh,
-                                                      float scale, uint64_t seed, uint32_t site,
+                                                      float scale, Seed seed_in, uint32_t site,
                                                       float* __restrict__ pooled, float* __restrict__ logits) {
+  const uint64_t seed = seed_in.ptr ? *seed_in.ptr : seed_in.value;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * 4 + warp;
   if (b >= B) return;
@@ -47,9 +48,10 @@ __global__ void __launch_bounds__(128) cls_fwd_kernel(const float* __restrict__ 
 // dlogits [B][L] -> dpre (fp16 [B][768], gradient wrt the pooler pre-activation), dWc, dbc (+=)
 __global__ void __launch_bounds__(128) cls_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ pooled,
                                                       const float* __restrict__ Wc, int B, int L, uint32_t thresh,
-                                                      float scale, uint64_t seed, uint32_t site, float oscale,
+                                                      float scale, Seed seed_in, uint32_t site, float oscale,
                                                       __half* __restrict__ dpre, float* __restrict__ dWc,
                                                       float* __restrict__ dbc) {
+  const uint64_t seed = seed_in.ptr ? *seed_in.ptr : seed_in.value;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * 4 + warp;
   if (b >= B) return;
@@ -116,7 +118,12 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float
                                                     float* __restrict__ v, __half* __restrict__ p16,
                                                     const uint8_t* __restrict__ decay_chunk, int64_t n4, float lr,
                                                     float b1, float b2, float eps, float wd, float step_size,
-                                                    float gscale, int zero_grad) {
+                                                    float gscale, int zero_grad,
+                                                    const float* __restrict__ hyper) {
+  if (hyper != nullptr) {
+    lr = hyper[0];
+    step_size = hyper[1];
+  }
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
     float4 gg = reinterpret_cast<float4*>(g)[i];
@@ -153,23 +160,25 @@ static inline void drop_params(float p, uint32_t& thresh, float& scale) {
   scale = 1.0f / (1.0f - p);
 }
 
-int cls_fwd(const float* pre, const float* Wc, const float* bc, int B, int L, float p, uint64_t seed, uint32_t site,
+int cls_fwd(const float* pre, const float* Wc, const float* bc, int B, int L, float p, Seed seed, uint32_t site,
             float* pooled, float* logits, cudaStream_t st) {
   MAGB_REQUIRE(L >= 1 && L <= 32, "classifier: num_labels=%d out of range [1,32]", L);
   uint32_t th; float sc;
   drop_params(p, th, sc);
   cls_fwd_kernel<<<(B + 3) / 4, 128, 0, st>>>(pre, Wc, bc, B, L, th, sc, seed, site, pooled, logits);
   MAGB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
-int cls_bwd(const float* dlogits, const float* pooled, const float* Wc, int B, int L, float p, uint64_t seed,
+int cls_bwd(const float* dlogits, const float* pooled, const float* Wc, int B, int L, float p, Seed seed,
             uint32_t site, float oscale, __half* dpre, float* dWc, float* dbc, cudaStream_t st) {
   MAGB_REQUIRE(L >= 1 && L <= 32, "classifier: num_labels=%d out of range [1,32]", L);
   uint32_t th; float sc;
   drop_params(p, th, sc);
   cls_bwd_kernel<<<(B + 3) / 4, 128, 0, st>>>(dlogits, pooled, Wc, B, L, th, sc, seed, site, oscale, dpre, dWc, dbc);
   MAGB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -177,11 +186,13 @@ int mse_loss(const float* logits, const float* labels, int n, float gscale, floa
              cudaStream_t st) {
   mse_kernel<<<1, 256, 0, st>>>(logits, labels, n, gscale, loss, dlogits);
   MAGB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
 int adamw_step(float* p, float* g, float* m, float* v, __half* p16, const uint8_t* decay_chunk, int64_t n, float lr,
-               float b1, float b2, float eps, float wd, int step, float gscale, int zero_grad, cudaStream_t st) {
+               float b1, float b2, float eps, float wd, int step, float gscale, int zero_grad, const float* hyper_dev,
+               cudaStream_t st) {
   MAGB_REQUIRE(n % 256 == 0, "adamw: flat buffer length must be a multiple of 256");
   MAGB_REQUIRE(step >= 1, "adamw: step must be >= 1");
   const double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
@@ -190,8 +201,9 @@ int adamw_step(float* p, float* g, float* m, float* v, __half* p16, const uint8_
   int blocks = (int)((n4 + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   adamw_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, p16, decay_chunk, n4, lr, b1, b2, eps, wd, step_size, gscale,
-                                       zero_grad);
+                                       zero_grad, hyper_dev);
   MAGB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 

@@ -7,6 +7,13 @@
 
 namespace magb200 {
 
+// Dropout seed of a step: by value, or read from device memory at kernel run time (ptr != null) so a
+// captured CUDA graph can be replayed with a fresh seed per step.
+struct Seed {
+  uint64_t value = 0;
+  const uint64_t* ptr = nullptr;
+};
+
 struct GemmProblem {
   const void* A = nullptr;   // K-major: [M][K] pitch lda ; MN-major: [K][M] pitch lda
   const void* B = nullptr;   // K-major: [N][K] pitch ldb ; MN-major: [K][N] pitch ldb
@@ -37,7 +44,7 @@ struct EmbedArgs {
   const float* word = nullptr; const float* pos = nullptr; const float* type = nullptr;
   const float* gamma = nullptr; const float* beta = nullptr;
   float eps = 1e-12f;
-  float p = 0.f; uint64_t seed = 0; uint32_t site = 0;
+  float p = 0.f; Seed seed; uint32_t site = 0;
   int V = 0, A = 0, KA = 896, T = 0, S = 0, vocab = 0, hidden = 768;
   float* emb32 = nullptr;            // [T][768]
   __half* amag = nullptr;            // [T][KA] or null
@@ -48,14 +55,14 @@ int embed_ln_bwd(const EmbedArgs& a, const float* dout, float oscale, float* dwo
 int mag_pack_inputs(const float* text, const float* visual, const float* acoustic, int V, int A, int KA, int T,
                     __half* amag, cudaStream_t st);
 int mag_tail_fwd(const float* G, const float* text32, const float* gamma, const float* beta, float beta_shift, float eps,
-                 float p, uint64_t seed, uint32_t site, int T, float* out32, __half* out16, cudaStream_t st);
+                 float p, Seed seed, uint32_t site, int T, float* out32, __half* out16, cudaStream_t st);
 int mag_tail_bwd(const float* dout, const float* G, const float* text32, const float* gamma, float beta_shift, float eps,
-                 float p, uint64_t seed, uint32_t site, int T, float oscale, __half* dG, float* dtext, float* dgamma,
+                 float p, Seed seed, uint32_t site, int T, float oscale, __half* dG, float* dtext, float* dgamma,
                  float* dbeta, float* dbias4, cudaStream_t st);
 int dropout_residual_ln_fwd(const float* pre, const float* res, const float* gamma, const float* beta, float eps, float p,
-                            uint64_t seed, uint32_t site, int T, float* y32, __half* y16, float* rstd, cudaStream_t st);
+                            Seed seed, uint32_t site, int T, float* y32, __half* y16, float* rstd, cudaStream_t st);
 int ln_bwd(const float* dy32, const float* y32, const float* gamma, const float* beta, const float* rstd, float p,
-           uint64_t seed, uint32_t site, int T, float oscale, float* dz32, __half* dpre, float* dgamma, float* dbeta,
+           Seed seed, uint32_t site, int T, float oscale, float* dz32, __half* dpre, float* dgamma, float* dbeta,
            float* dbias, cudaStream_t st);
 int colsum_f16(const __half* in, int T, int N, float oscale, float* out, cudaStream_t st);
 int cast_f32_f16(const float* in, __half* out, int64_t n, cudaStream_t st);
@@ -63,23 +70,24 @@ int mag_pack_weights(const float* W_hv, const float* W_ha, const float* W_v, con
                      __half* Bm, cudaStream_t st);
 int mag_unpack_wgrad(const float* dB, int V, int A, int KA, float* dW_hv, float* dW_ha, float* dW_v, float* dW_a,
                      cudaStream_t st);
-int dropout_mask(uint8_t* out, int64_t n, float p, uint64_t seed, uint32_t site, cudaStream_t st);
+int dropout_mask(uint8_t* out, int64_t n, float p, Seed seed, uint32_t site, cudaStream_t st);
 
 
 // ---------------------------------------------------------------- attention.cu
-int sdpa_fwd(const __half* qkv, const int64_t* mask, int B, int S, int heads, int head_dim, float p, uint64_t seed,
+int sdpa_fwd(const __half* qkv, const int64_t* mask, int B, int S, int heads, int head_dim, float p, Seed seed,
              uint32_t site, __half* ctx, cudaStream_t st);
 int sdpa_bwd(const __half* qkv, const __half* dctx, const int64_t* mask, int B, int S, int heads, int head_dim, float p,
-             uint64_t seed, uint32_t site, __half* dqkv, cudaStream_t st);
+             Seed seed, uint32_t site, __half* dqkv, cudaStream_t st);
 
 // ---------------------------------------------------------------- head_optim.cu
-int cls_fwd(const float* pre, const float* Wc, const float* bc, int B, int L, float p, uint64_t seed, uint32_t site,
+int cls_fwd(const float* pre, const float* Wc, const float* bc, int B, int L, float p, Seed seed, uint32_t site,
             float* pooled, float* logits, cudaStream_t st);
-int cls_bwd(const float* dlogits, const float* pooled, const float* Wc, int B, int L, float p, uint64_t seed,
+int cls_bwd(const float* dlogits, const float* pooled, const float* Wc, int B, int L, float p, Seed seed,
             uint32_t site, float oscale, __half* dpre, float* dWc, float* dbc, cudaStream_t st);
 int mse_loss(const float* logits, const float* labels, int n, float gscale, float* loss, float* dlogits, cudaStream_t st);
 int adamw_step(float* p, float* g, float* m, float* v, __half* p16, const uint8_t* decay_chunk, int64_t n, float lr,
-               float b1, float b2, float eps, float wd, int step, float gscale, int zero_grad, cudaStream_t st);
+               float b1, float b2, float eps, float wd, int step, float gscale, int zero_grad, const float* hyper_dev,
+               cudaStream_t st);
 
 }  // namespace magb200
 

@@ -156,13 +156,14 @@ int bert_forward(const magb200_bert_dims& d, const int64_t* off, const float* P,
   BertWs w = carve_ws(d, workspace);
   MAGB_REQUIRE(ws_bytes >= w.bytes, "bert_forward: workspace too small (%zu < %zu)", ws_bytes, w.bytes);
   const int B = d.batch, S = d.seq, T = B * S, H = d.hidden, I = d.inter;
+  const Seed sd{d.seed, d.seed_dev};
 
   // BertEmbeddings (+ packing of the MAG GEMM operand)                         bert.py:211-216
   EmbedArgs e;
   e.ids = ids; e.tt = tt; e.visual = visual; e.acoustic = acoustic;
   e.word = P + off[MAGB200_OFF_WORD]; e.pos = P + off[MAGB200_OFF_POS]; e.type = P + off[MAGB200_OFF_TYPE];
   e.gamma = P + off[MAGB200_OFF_EMB_LN_W]; e.beta = P + off[MAGB200_OFF_EMB_LN_B];
-  e.eps = d.ln_eps; e.p = d.p_hidden; e.seed = d.seed; e.site = SITE_EMB;
+  e.eps = d.ln_eps; e.p = d.p_hidden; e.seed = sd; e.site = SITE_EMB;
   e.V = d.visual_dim; e.A = d.acoustic_dim; e.KA = d.ka; e.T = T; e.S = S; e.vocab = d.vocab;
   e.emb32 = w.emb32; e.amag = w.amag16;
   RUN(embed_ln_fwd(e, st));
@@ -170,29 +171,29 @@ int bert_forward(const magb200_bert_dims& d, const int64_t* off, const float* P,
   RUN(linear_fwd(w.amag16, d.ka, P16 + off[MAGB200_OFF_MAG_PACKED16], T, 4 * H, d.ka, P + off[MAGB200_OFF_MAG_BIAS4],
                  EPI_STORE_F32, w.G32, nullptr, 4 * H, st, 2 * H, H));
   RUN(mag_tail_fwd(w.G32, w.emb32, P + off[MAGB200_OFF_MAG_LN_W], P + off[MAGB200_OFF_MAG_LN_B], d.beta_shift,
-                   d.mag_ln_eps, d.p_mag, d.seed, SITE_MAG, T, w.x32[0], w.x16[0], st));
+                   d.mag_ln_eps, d.p_mag, sd, SITE_MAG, T, w.x32[0], w.x16[0], st));
   // BertEncoder                                                                  bert.py:221-229
   for (int l = 0; l < d.layers; ++l) {
     const int64_t* o = off + MAGB200_OFF_LAYER0 + (int64_t)l * MAGB200_OFF_PER_LAYER;
     LayerWs& L = w.layer[l];
     RUN(linear_fwd(w.x16[l], H, P16 + o[MAGB200_LOFF_QKV_W], T, 3 * H, H, P + o[MAGB200_LOFF_QKV_B], EPI_STORE_F16,
                    L.qkv16, nullptr, 3 * H, st));
-    RUN(sdpa_fwd(L.qkv16, mask, B, S, d.heads, H / d.heads, d.p_attn, d.seed, site_attn_prob(l), L.ctx16, st));
+    RUN(sdpa_fwd(L.qkv16, mask, B, S, d.heads, H / d.heads, d.p_attn, sd, site_attn_prob(l), L.ctx16, st));
     RUN(linear_fwd(L.ctx16, H, P16 + o[MAGB200_LOFF_AO_W], T, H, H, P + o[MAGB200_LOFF_AO_B], EPI_STORE_F32, w.pre32,
                    nullptr, H, st));
     RUN(dropout_residual_ln_fwd(w.pre32, w.x32[l], P + o[MAGB200_LOFF_LN1_W], P + o[MAGB200_LOFF_LN1_B], d.ln_eps,
-                                d.p_hidden, d.seed, site_attn_out(l), T, L.a32, L.a16, L.rstd1, st));
+                                d.p_hidden, sd, site_attn_out(l), T, L.a32, L.a16, L.rstd1, st));
     RUN(linear_fwd(L.a16, H, P16 + o[MAGB200_LOFF_F1_W], T, I, H, P + o[MAGB200_LOFF_F1_B], EPI_GELU_F16, L.g16, L.u16,
                    I, st));
     RUN(linear_fwd(L.g16, I, P16 + o[MAGB200_LOFF_F2_W], T, H, I, P + o[MAGB200_LOFF_F2_B], EPI_STORE_F32, w.pre32,
                    nullptr, H, st));
     RUN(dropout_residual_ln_fwd(w.pre32, L.a32, P + o[MAGB200_LOFF_LN2_W], P + o[MAGB200_LOFF_LN2_B], d.ln_eps,
-                                d.p_hidden, d.seed, site_ffn_out(l), T, w.x32[l + 1], w.x16[l + 1], L.rstd2, st));
+                                d.p_hidden, sd, site_ffn_out(l), T, w.x32[l + 1], w.x16[l + 1], L.rstd2, st));
   }
   // BertPooler on the CLS rows (row pitch S*H) + classifier                       bert.py:231, 304-307
   RUN(linear_fwd(w.x16[d.layers], S * H, P16 + off[MAGB200_OFF_POOL_W], B, H, H, P + off[MAGB200_OFF_POOL_B],
                  EPI_STORE_F32, w.poolpre32, nullptr, H, st));
-  RUN(cls_fwd(w.poolpre32, P + off[MAGB200_OFF_CLS_W], P + off[MAGB200_OFF_CLS_B], B, d.num_labels, d.p_cls, d.seed,
+  RUN(cls_fwd(w.poolpre32, P + off[MAGB200_OFF_CLS_W], P + off[MAGB200_OFF_CLS_B], B, d.num_labels, d.p_cls, sd,
               SITE_CLS, w.pooled32, logits, st));
   return 0;
 }
@@ -206,9 +207,10 @@ int bert_backward(const magb200_bert_dims& d, const int64_t* off, const float* P
   MAGB_REQUIRE(ws_bytes >= w.bytes, "bert_backward: workspace too small (%zu < %zu)", ws_bytes, w.bytes);
   const int B = d.batch, S = d.seq, T = B * S, H = d.hidden, I = d.inter;
   const float us = 1.0f / d.grad_scale;   // parameter gradients are stored unscaled
+  const Seed sd{d.seed, d.seed_dev};
 
   // classifier + pooler                                                         bert.py:304-307, 231
-  RUN(cls_bwd(dlogits_scaled, w.pooled32, P + off[MAGB200_OFF_CLS_W], B, d.num_labels, d.p_cls, d.seed, SITE_CLS,
+  RUN(cls_bwd(dlogits_scaled, w.pooled32, P + off[MAGB200_OFF_CLS_W], B, d.num_labels, d.p_cls, sd, SITE_CLS,
               us, w.dpool16, G + off[MAGB200_OFF_CLS_W], G + off[MAGB200_OFF_CLS_B], st));
   MAGB_CHECK_CUDA(cudaMemsetAsync(w.dy32, 0, (size_t)T * H * sizeof(float), st));
   RUN(linear_dgrad(w.dpool16, H, P16 + off[MAGB200_OFF_POOL_W], H, B, H, H, EPI_STORE_F32, w.dy32, nullptr, S * H, st));
@@ -219,7 +221,7 @@ int bert_backward(const magb200_bert_dims& d, const int64_t* off, const float* P
     const int64_t* o = off + MAGB200_OFF_LAYER0 + (int64_t)l * MAGB200_OFF_PER_LAYER;
     LayerWs& L = w.layer[l];
     // BertOutput: LayerNorm(dropout(dense(g)) + a)
-    RUN(ln_bwd(w.dy32, w.x32[l + 1], P + o[MAGB200_LOFF_LN2_W], P + o[MAGB200_LOFF_LN2_B], L.rstd2, d.p_hidden, d.seed,
+    RUN(ln_bwd(w.dy32, w.x32[l + 1], P + o[MAGB200_LOFF_LN2_W], P + o[MAGB200_LOFF_LN2_B], L.rstd2, d.p_hidden, sd,
                site_ffn_out(l), T, us, w.dr32, w.dpre16, G + o[MAGB200_LOFF_LN2_W], G + o[MAGB200_LOFF_LN2_B],
                G + o[MAGB200_LOFF_F2_B], st));
     RUN(linear_wgrad(w.dpre16, H, L.g16, I, T, H, I, G + o[MAGB200_LOFF_F2_W], I, 1, us, st));
@@ -229,20 +231,20 @@ int bert_backward(const magb200_bert_dims& d, const int64_t* off, const float* P
     RUN(linear_wgrad(w.du16, I, L.a16, H, T, I, H, G + o[MAGB200_LOFF_F1_W], H, 1, us, st));
     RUN(linear_dgrad(w.du16, I, P16 + o[MAGB200_LOFF_F1_W], H, T, H, I, EPI_STORE_F32, w.dr32, w.dr32, H, st));
     // BertSelfOutput: LayerNorm(dropout(dense(ctx)) + x)
-    RUN(ln_bwd(w.dr32, L.a32, P + o[MAGB200_LOFF_LN1_W], P + o[MAGB200_LOFF_LN1_B], L.rstd1, d.p_hidden, d.seed,
+    RUN(ln_bwd(w.dr32, L.a32, P + o[MAGB200_LOFF_LN1_W], P + o[MAGB200_LOFF_LN1_B], L.rstd1, d.p_hidden, sd,
                site_attn_out(l), T, us, w.dy32, w.dpre16, G + o[MAGB200_LOFF_LN1_W], G + o[MAGB200_LOFF_LN1_B],
                G + o[MAGB200_LOFF_AO_B], st));
     RUN(linear_wgrad(w.dpre16, H, L.ctx16, H, T, H, H, G + o[MAGB200_LOFF_AO_W], H, 4, us, st));
     RUN(linear_dgrad(w.dpre16, H, P16 + o[MAGB200_LOFF_AO_W], H, T, H, H, EPI_STORE_F16, w.dctx16, nullptr, H, st));
     // BertSelfAttention
-    RUN(sdpa_bwd(L.qkv16, w.dctx16, mask, B, S, d.heads, H / d.heads, d.p_attn, d.seed, site_attn_prob(l), w.dqkv16, st));
+    RUN(sdpa_bwd(L.qkv16, w.dctx16, mask, B, S, d.heads, H / d.heads, d.p_attn, sd, site_attn_prob(l), w.dqkv16, st));
     RUN(colsum_f16(w.dqkv16, T, 3 * H, us, G + o[MAGB200_LOFF_QKV_B], st));
     RUN(linear_wgrad(w.dqkv16, 3 * H, w.x16[l], H, T, 3 * H, H, G + o[MAGB200_LOFF_QKV_W], H, 2, us, st));
     RUN(linear_dgrad(w.dqkv16, 3 * H, P16 + o[MAGB200_LOFF_QKV_W], H, T, H, 3 * H, EPI_STORE_F32, w.dy32, w.dy32, H, st));
   }
 
   // MAG (modeling.py:25-51)
-  RUN(mag_tail_bwd(w.dy32, w.G32, w.emb32, P + off[MAGB200_OFF_MAG_LN_W], d.beta_shift, d.mag_ln_eps, d.p_mag, d.seed,
+  RUN(mag_tail_bwd(w.dy32, w.G32, w.emb32, P + off[MAGB200_OFF_MAG_LN_W], d.beta_shift, d.mag_ln_eps, d.p_mag, sd,
                    SITE_MAG, T, us, w.dG16, w.dr32, G + off[MAGB200_OFF_MAG_LN_W], G + off[MAGB200_OFF_MAG_LN_B],
                    G + off[MAGB200_OFF_MAG_BIAS4], st));
   MAGB_CHECK_CUDA(cudaMemsetAsync(w.dBmag32, 0, (size_t)4 * H * d.ka * sizeof(float), st));
@@ -257,7 +259,7 @@ int bert_backward(const magb200_bert_dims& d, const int64_t* off, const float* P
   e.ids = ids; e.tt = tt;
   e.word = P + off[MAGB200_OFF_WORD]; e.pos = P + off[MAGB200_OFF_POS]; e.type = P + off[MAGB200_OFF_TYPE];
   e.gamma = P + off[MAGB200_OFF_EMB_LN_W]; e.beta = P + off[MAGB200_OFF_EMB_LN_B];
-  e.eps = d.ln_eps; e.p = d.p_hidden; e.seed = d.seed; e.site = SITE_EMB; e.T = T; e.S = S; e.vocab = d.vocab;
+  e.eps = d.ln_eps; e.p = d.p_hidden; e.seed = sd; e.site = SITE_EMB; e.T = T; e.S = S; e.vocab = d.vocab;
   RUN(embed_ln_bwd(e, w.dr32, us, G + off[MAGB200_OFF_WORD], G + off[MAGB200_OFF_POS], G + off[MAGB200_OFF_TYPE],
                    G + off[MAGB200_OFF_EMB_LN_W], G + off[MAGB200_OFF_EMB_LN_B], st));
   return 0;

@@ -118,8 +118,9 @@ __global__ void __launch_bounds__(128) embed_ln_fwd_kernel(
     const int64_t* __restrict__ ids, const int64_t* __restrict__ tt, const float* __restrict__ visual,
     const float* __restrict__ acoustic, const float* __restrict__ word, const float* __restrict__ pos,
     const float* __restrict__ type, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-    uint32_t thresh, float scale, uint64_t seed, uint32_t site, int V, int A, int KA, int T, int S, int vocab,
+    uint32_t thresh, float scale, Seed seed_in, uint32_t site, int V, int A, int KA, int T, int S, int vocab,
     float* __restrict__ emb32, __half* __restrict__ amag) {
+  const uint64_t seed = seed_in.ptr ? *seed_in.ptr : seed_in.value;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * 4 + warp;
   if (t >= T) return;
@@ -180,9 +181,10 @@ __global__ void __launch_bounds__(128) mag_pack_inputs_kernel(const float* __res
 __global__ void __launch_bounds__(128) embed_ln_bwd_kernel(
     const float* __restrict__ dout, const int64_t* __restrict__ ids, const int64_t* __restrict__ tt,
     const float* __restrict__ word, const float* __restrict__ pos, const float* __restrict__ type,
-    const float* __restrict__ gamma, float eps, uint32_t thresh, float scale, uint64_t seed, uint32_t site, int T,
+    const float* __restrict__ gamma, float eps, uint32_t thresh, float scale, Seed seed_in, uint32_t site, int T,
     int S, int vocab, float oscale, float* __restrict__ dword, float* __restrict__ dpos, float* __restrict__ dtype,
     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const uint64_t seed = seed_in.ptr ? *seed_in.ptr : seed_in.value;
   __shared__ float acc[2 * H];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   acc_zero(acc, 2 * H);
@@ -262,9 +264,10 @@ __device__ __forceinline__ void mag_row_forward(const float* __restrict__ Gt, co
 __global__ void __launch_bounds__(128) mag_tail_fwd_kernel(const float* __restrict__ G, const float* __restrict__ text32,
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float beta_shift,
-                                                           float eps, uint32_t thresh, float scale, uint64_t seed,
+                                                           float eps, uint32_t thresh, float scale, Seed seed_in,
                                                            uint32_t site, int T, float* __restrict__ out32,
                                                            __half* __restrict__ out16) {
+  const uint64_t seed = seed_in.ptr ? *seed_in.ptr : seed_in.value;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * 4 + warp;
   if (t >= T) return;
@@ -288,9 +291,10 @@ __global__ void __launch_bounds__(128) mag_tail_fwd_kernel(const float* __restri
 
 __global__ void __launch_bounds__(128) mag_tail_bwd_kernel(
     const float* __restrict__ dout, const float* __restrict__ G, const float* __restrict__ text32,
-    const float* __restrict__ gamma, float beta_shift, float eps, uint32_t thresh, float scale, uint64_t seed,
+    const float* __restrict__ gamma, float beta_shift, float eps, uint32_t thresh, float scale, Seed seed_in,
     uint32_t site, int T, float oscale, __half* __restrict__ dG, float* __restrict__ dtext,
     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias4) {
+  const uint64_t seed = seed_in.ptr ? *seed_in.ptr : seed_in.value;
   __shared__ float acc[6 * H];   // dgamma | dbeta | dbias of the four gate-GEMM column blocks
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   acc_zero(acc, 6 * H);
@@ -363,8 +367,9 @@ __global__ void __launch_bounds__(128) mag_tail_bwd_kernel(
 // y = LayerNorm(dropout(pre) + res)   (BertSelfOutput / BertOutput; XLNet post_attention / ff)
 __global__ void __launch_bounds__(128) dropout_residual_ln_fwd_kernel(
     const float* __restrict__ pre, const float* __restrict__ res, const float* __restrict__ gamma,
-    const float* __restrict__ beta, float eps, uint32_t thresh, float scale, uint64_t seed, uint32_t site, int T,
+    const float* __restrict__ beta, float eps, uint32_t thresh, float scale, Seed seed_in, uint32_t site, int T,
     float* __restrict__ y32, __half* __restrict__ y16, float* __restrict__ rstd_out) {
+  const uint64_t seed = seed_in.ptr ? *seed_in.ptr : seed_in.value;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * 4 + warp;
   if (t >= T) return;
@@ -393,10 +398,11 @@ __global__ void __launch_bounds__(128) dropout_residual_ln_fwd_kernel(
 __global__ void __launch_bounds__(128) ln_bwd_kernel(const float* __restrict__ dy32, const float* __restrict__ y32,
                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                      const float* __restrict__ rstd_in, uint32_t thresh, float scale,
-                                                     uint64_t seed, uint32_t site, int T, float oscale,
+                                                     Seed seed_in, uint32_t site, int T, float oscale,
                                                      float* __restrict__ dz32, __half* __restrict__ dpre,
                                                      float* __restrict__ dgamma,
                                                      float* __restrict__ dbeta, float* __restrict__ dbias) {
+  const uint64_t seed = seed_in.ptr ? *seed_in.ptr : seed_in.value;
   __shared__ float acc[3 * H];   // dgamma | dbeta | dbias
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   Row g, b;
@@ -522,7 +528,8 @@ __global__ void mag_unpack_wgrad_kernel(const float* __restrict__ dB, int V, int
 
 // --------------------------------------------------------------------------------------------
 // Debug/test hook: the keep-mask (1/0 bytes) the kernels use for (seed, site) over n elements.
-__global__ void dropout_mask_kernel(uint8_t* __restrict__ out, int64_t n, uint32_t thresh, uint64_t seed, uint32_t site) {
+__global__ void dropout_mask_kernel(uint8_t* __restrict__ out, int64_t n, uint32_t thresh, Seed seed_in, uint32_t site) {
+  const uint64_t seed = seed_in.ptr ? *seed_in.ptr : seed_in.value;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (n + 3) / 4; i += (int64_t)gridDim.x * blockDim.x) {
     const uint4 u = philox4x32(seed, site, (uint64_t)i);
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -548,6 +555,7 @@ int embed_ln_fwd(const EmbedArgs& a, cudaStream_t st) {
                                                      a.beta, a.eps, th, sc, a.seed, a.site, a.V, a.A, a.KA, a.T, a.S,
                                                      a.vocab, a.emb32, a.amag);
   MAGB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -556,6 +564,7 @@ int mag_pack_inputs(const float* text, const float* visual, const float* acousti
   MAGB_REQUIRE(V + A <= KA - H, "mag: V+A=%d does not fit KA=%d", V + A, KA);
   mag_pack_inputs_kernel<<<(T + 3) / 4, 128, 0, st>>>(text, visual, acoustic, V, A, KA, T, amag);
   MAGB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -572,49 +581,54 @@ int embed_ln_bwd(const EmbedArgs& a, const float* dout, float oscale, float* dwo
                                                       a.seed, a.site, a.T, a.S, a.vocab, oscale, dword, dpos, dtype,
                                                       dgamma, dbeta);
   MAGB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
 int mag_tail_fwd(const float* G, const float* text32, const float* gamma, const float* beta, float beta_shift, float eps,
-                 float p, uint64_t seed, uint32_t site, int T, float* out32, __half* out16, cudaStream_t st) {
+                 float p, Seed seed, uint32_t site, int T, float* out32, __half* out16, cudaStream_t st) {
   uint32_t th; float sc;
   drop_params(p, th, sc);
   mag_tail_fwd_kernel<<<(T + 3) / 4, 128, 0, st>>>(G, text32, gamma, beta, beta_shift, eps, th, sc, seed, site, T, out32,
                                                    out16);
   MAGB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
 int mag_tail_bwd(const float* dout, const float* G, const float* text32, const float* gamma, float beta_shift, float eps,
-                 float p, uint64_t seed, uint32_t site, int T, float oscale, __half* dG, float* dtext, float* dgamma,
+                 float p, Seed seed, uint32_t site, int T, float oscale, __half* dG, float* dtext, float* dgamma,
                  float* dbeta, float* dbias4, cudaStream_t st) {
   uint32_t th; float sc;
   drop_params(p, th, sc);
   mag_tail_bwd_kernel<<<grid_rows(T), 128, 0, st>>>(dout, G, text32, gamma, beta_shift, eps, th, sc, seed, site, T, oscale,
                                                     dG, dtext, dgamma, dbeta, dbias4);
   MAGB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
 int dropout_residual_ln_fwd(const float* pre, const float* res, const float* gamma, const float* beta, float eps, float p,
-                            uint64_t seed, uint32_t site, int T, float* y32, __half* y16, float* rstd,
+                            Seed seed, uint32_t site, int T, float* y32, __half* y16, float* rstd,
                             cudaStream_t st) {
   uint32_t th; float sc;
   drop_params(p, th, sc);
   dropout_residual_ln_fwd_kernel<<<(T + 3) / 4, 128, 0, st>>>(pre, res, gamma, beta, eps, th, sc, seed, site, T, y32,
                                                               y16, rstd);
   MAGB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
 int ln_bwd(const float* dy32, const float* y32, const float* gamma, const float* beta, const float* rstd, float p,
-           uint64_t seed, uint32_t site, int T, float oscale, float* dz32, __half* dpre, float* dgamma, float* dbeta,
+           Seed seed, uint32_t site, int T, float oscale, float* dz32, __half* dpre, float* dgamma, float* dbeta,
            float* dbias, cudaStream_t st) {
   uint32_t th; float sc;
   drop_params(p, th, sc);
   ln_bwd_kernel<<<grid_rows(T), 128, 0, st>>>(dy32, y32, gamma, beta, rstd, th, sc, seed, site, T, oscale, dz32, dpre,
                                               dgamma, dbeta, dbias);
   MAGB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -623,6 +637,7 @@ int colsum_f16(const __half* in, int T, int N, float oscale, float* out, cudaStr
   dim3 grid((N + 63) / 64, T >= 512 ? 16 : 4);
   colsum_f16_kernel<<<grid, 256, 0, st>>>(in, T, N, oscale, out);
   MAGB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -634,6 +649,7 @@ int cast_f32_f16(const float* in, __half* out, int64_t n, cudaStream_t st) {
   if (blocks < 1) blocks = 1;
   cast_f32_f16_kernel<<<blocks, 256, 0, st>>>(in, out, n4);
   MAGB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -642,6 +658,7 @@ int mag_pack_weights(const float* W_hv, const float* W_ha, const float* W_v, con
   MAGB_REQUIRE(V + A <= KA - H, "mag: V+A=%d does not fit KA=%d", V + A, KA);
   mag_pack_weights_kernel<<<4 * H, 128, 0, st>>>(W_hv, W_ha, W_v, W_a, V, A, KA, Bm);
   MAGB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -649,14 +666,16 @@ int mag_unpack_wgrad(const float* dB, int V, int A, int KA, float* dW_hv, float*
                      cudaStream_t st) {
   mag_unpack_wgrad_kernel<<<4 * H, 128, 0, st>>>(dB, V, A, KA, dW_hv, dW_ha, dW_v, dW_a);
   MAGB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
-int dropout_mask(uint8_t* out, int64_t n, float p, uint64_t seed, uint32_t site, cudaStream_t st) {
+int dropout_mask(uint8_t* out, int64_t n, float p, Seed seed, uint32_t site, cudaStream_t st) {
   uint32_t th; float sc;
   drop_params(p, th, sc);
   dropout_mask_kernel<<<256, 256, 0, st>>>(out, n, th, seed, site);
   MAGB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 

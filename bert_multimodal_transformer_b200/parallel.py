@@ -1,0 +1,42 @@
+"""Host-side data-parallel plumbing: one process per GPU, batch sharded by
+contiguous slices, ONE collective per step -- a sum all-reduce of the flat gradient buffer; the mean
+over ranks is folded into the AdamW kernel's grad_unscale.  torch.distributed is the transport (NCCL over
+NVLink on GPUs; gloo in the CPU tests)."""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def world_info(group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def shard_slice(global_batch: int, rank: int, world: int) -> slice:
+    """Contiguous B/world slice of the global batch for `rank` (config 3: 128 -> 16 per GPU on 8 GPUs)."""
+    if global_batch % world != 0:
+        raise ValueError(f"global batch {global_batch} is not divisible by world size {world}")
+    per = global_batch // world
+    return slice(rank * per, (rank + 1) * per)
+
+
+def shard_batch(batch: dict, rank: int, world: int) -> dict:
+    n = next(iter(batch.values())).shape[0]
+    s = shard_slice(n, rank, world)
+    return {k: v[s] for k, v in batch.items()}
+
+
+def allreduce_sum_(flat_grads: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place sum over ranks of the flat gradient buffer (a no-op for a single process)."""
+    _, world = world_info(group)
+    if world > 1:
+        dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group)
+    return flat_grads
+
+
+def grad_unscale(world: int) -> float:
+    """Each rank's loss is a MEAN over its local batch (multimodal_driver.py:371-373), so the global-batch
+    gradient is the mean of the per-rank gradients: sum-all-reduce, then multiply by 1/world."""
+    return 1.0 / float(world)

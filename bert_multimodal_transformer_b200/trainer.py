@@ -1,0 +1,286 @@
+"""Training / inference steps of MAG-BERT as single CUDA-graph replays.
+
+The reference's hot loop (multimodal_driver.py:354-388) is, per batch: H2D copy of six small tensors,
+forward, MSE loss, backward, AdamW step, LR-schedule step, zero_grad, `loss.item()`.  At bs=48, S=50
+the whole step is ~1.3 TFLOP spread over ~300 kernels, so launch latency dominates unless the step
+is replayed as one graph.  `MagBertTrainer.train_step` does exactly that:
+
+    pinned host batch --H2D--> [ forward | mse | backward | (NCCL all-reduce) | AdamW+zero_grad+fp16 refresh ] --D2H--> loss
+
+Everything that changes from step to step (dropout seed, learning rate, Adam bias correction) is read
+by the kernels from a small device control block that is part of the H2D copy, so one captured graph
+serves every step.  Data parallelism: one process per GPU, each rank runs this on
+its own slice of the batch; the only collective is the gradient all-reduce over the flat buffer.
+"""
+from __future__ import annotations
+
+import math
+from ctypes import byref, c_void_p
+
+import numpy as np
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+from .engine import BertEngine
+from .parallel import allreduce_sum_, grad_unscale
+
+
+def linear_schedule(step: int, warmup: int, total: int) -> float:
+    """transformers.get_linear_schedule_with_warmup lambda (multimodal_driver.py:346-350)."""
+    if step < warmup:
+        return float(step) / float(max(1, warmup))
+    return max(0.0, float(total - step) / float(max(1, total - warmup)))
+
+
+class MagBertTrainer:
+    def __init__(self, model, batch_size: int, seq_len: int, lr: float = 1e-5, weight_decay: float = 0.01,
+                 betas=(0.9, 0.999), eps: float = 1e-6, warmup_steps: int = 0, total_steps: int = 0,
+                 use_cuda_graph: bool = True, process_group=None, seed: int = 0):
+        model._ensure_bound()
+        self.model = model
+        self.eng: BertEngine = model._engine
+        eng = self.eng
+        self.B, self.S = batch_size, seq_len
+        self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
+        self.warmup_steps, self.total_steps = warmup_steps, total_steps
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        dev = eng.flat.device
+        self.dev = dev
+        n = eng.layout.total
+        self.grads = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.decay = eng.layout.decay_chunks().to(dev)
+        self.step_count = 0
+        self._gen = torch.Generator().manual_seed(seed)
+        B, S, V, A, Lb = batch_size, seq_len, eng.visual_dim, eng.acoustic_dim, eng.num_labels
+        # static device inputs + pinned host staging
+        spec = dict(input_ids=((B, S), torch.int64), token_type_ids=((B, S), torch.int64),
+                    attention_mask=((B, S), torch.int64), visual=((B, S, V), torch.float32),
+                    acoustic=((B, S, A), torch.float32), labels=((B * Lb,), torch.float32))
+        self.dev_in = {k: torch.zeros(s, dtype=t, device=dev) for k, (s, t) in spec.items()}
+        # two pinned staging slots: while the GPU runs step k out of slot k%2, the host fills slot (k+1)%2
+        self.NSLOT = 2
+        self.slots = [{k: torch.zeros(s, dtype=t).pin_memory() for k, (s, t) in spec.items()} for _ in range(self.NSLOT)]
+        self.slots_np = [{k: v.numpy() for k, v in sl.items()} for sl in self.slots]
+        self.slot = 0
+        self.host_in = self.slots[0]
+        # per-step control block (device words the kernels read): dropout seed, lr, Adam step size
+        self.host_seed = [torch.zeros(1, dtype=torch.int64).pin_memory() for _ in range(self.NSLOT)]
+        self.dev_seed = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.host_hyper = [torch.zeros(2, dtype=torch.float32).pin_memory() for _ in range(self.NSLOT)]
+        self.dev_hyper = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.logits = torch.zeros(B, Lb, dtype=torch.float32, device=dev)
+        self.dlogits = torch.zeros(B, Lb, dtype=torch.float32, device=dev)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.host_loss = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(self.NSLOT)]
+        self.host_logits = torch.zeros(B, Lb, dtype=torch.float32).pin_memory()
+        self.done = [torch.cuda.Event() for _ in range(self.NSLOT)]
+        self.train_dims = eng.dims(B, S, True, 0)
+        self.train_dims.seed_dev = self.dev_seed.data_ptr()
+        self.eval_dims = eng.dims(B, S, False, 0)
+        lib = L.load()
+        self.ws = torch.empty(lib.magb200_bert_workspace_bytes(byref(self.train_dims)), dtype=torch.uint8, device=dev)
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.slots[0].values()) + 8 + 8
+        self.d2h_bytes = 4
+        self.use_graph = use_cuda_graph
+        self._train_graph = [None] * self.NSLOT     # one captured graph per staging slot (fixed memcpy sources)
+        self._eval_graph = [None] * self.NSLOT
+        self._train_graph_resident = None
+        self._eval_graph_resident = None
+        self.stream = torch.cuda.Stream(device=dev)
+        eng.refresh_operands()
+        self.kernel_launches_per_train_step = None
+
+    # ------------------------------------------------------------------ device-side step bodies
+    def _h2d(self, slot, with_labels=True):
+        for k, d in self.dev_in.items():
+            if k == "labels" and not with_labels:
+                continue
+            d.copy_(self.slots[slot][k], non_blocking=True)
+
+    def _train_body(self, transfers=True, slot=0):
+        eng, lib = self.eng, L.load()
+        st = L.current_stream()
+        if transfers:
+            self._h2d(slot)
+        self.dev_seed.copy_(self.host_seed[slot], non_blocking=True)
+        self.dev_hyper.copy_(self.host_hyper[slot], non_blocking=True)
+        i = self.dev_in
+        eng.forward(self.train_dims, self.ws, i["input_ids"], i["token_type_ids"], i["attention_mask"], i["visual"],
+                    i["acoustic"], self.logits)
+        L.check(lib.magb200_mse_loss(L.ptr(self.logits), L.ptr(i["labels"]), self.B * eng.num_labels, eng.grad_scale,
+                                     L.ptr(self.loss), L.ptr(self.dlogits), st))
+        eng.backward(self.train_dims, self.ws, i["input_ids"], i["token_type_ids"], i["attention_mask"], self.dlogits,
+                     self.grads)
+        if self.world > 1:
+            allreduce_sum_(self.grads, self.pg)
+        L.check(lib.magb200_adamw_step(L.ptr(eng.flat), L.ptr(self.grads), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq),
+                                       L.ptr(eng.flat16), L.ptr(self.decay), eng.layout.total, self.lr, self.betas[0],
+                                       self.betas[1], self.eps, self.wd, 1, grad_unscale(self.world), 1, L.ptr(self.dev_hyper),
+                                       st))
+        o = eng.offsets
+        f = eng.flat
+        L.check(lib.magb200_mag_pack_weights(
+            c_void_p(f.data_ptr() + 4 * o[L.OFF_MAG_WHV]), c_void_p(f.data_ptr() + 4 * o[L.OFF_MAG_WHA]),
+            c_void_p(f.data_ptr() + 4 * o[L.OFF_MAG_WV]), c_void_p(f.data_ptr() + 4 * o[L.OFF_MAG_WA]),
+            eng.visual_dim, eng.acoustic_dim, eng.ka, c_void_p(eng.flat16.data_ptr() + 2 * o[L.OFF_MAG_PACKED16]), st))
+        if transfers:
+            self.host_loss[slot].copy_(self.loss, non_blocking=True)
+
+    def _eval_body(self, transfers=True, slot=0):
+        eng = self.eng
+        if transfers:
+            self._h2d(slot, with_labels=False)
+        i = self.dev_in
+        eng.forward(self.eval_dims, self.ws, i["input_ids"], i["token_type_ids"], i["attention_mask"], i["visual"],
+                    i["acoustic"], self.logits)
+        if transfers:
+            self.host_logits.copy_(self.logits, non_blocking=True)
+
+    def _capture(self, body):
+        # warm up on the side stream (descriptor caches, func attributes), then capture
+        s = self.stream
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            body()
+        s.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            body()
+        return g
+
+    # ------------------------------------------------------------------ host API
+    def _stage(self, input_ids, visual, acoustic, attention_mask, token_type_ids, labels=None):
+        """Host batch -> the current pinned staging slot.  Plain single-threaded memcpy through numpy
+        (torch.Tensor.copy_ spins up the intra-op thread pool, which costs milliseconds on a busy host)."""
+        self.done[self.slot].synchronize()          # the previous step that read this slot has finished
+        h = self.slots_np[self.slot]
+
+        def put(name, t, dtype):
+            if torch.is_tensor(t):
+                t = t.detach()
+                if t.is_cuda:
+                    t = t.cpu()
+                t = t.to(dtype).contiguous().numpy()
+            np.copyto(h[name], np.asarray(t).reshape(h[name].shape), casting="unsafe")
+
+        put("input_ids", input_ids, torch.int64)
+        put("visual", visual, torch.float32)
+        put("acoustic", acoustic, torch.float32)
+        if attention_mask is None:
+            h["attention_mask"].fill(1)
+        else:
+            put("attention_mask", attention_mask, torch.int64)
+        if token_type_ids is None:
+            h["token_type_ids"].fill(0)
+        else:
+            put("token_type_ids", token_type_ids, torch.int64)
+        if labels is not None:
+            put("labels", labels, torch.float32)
+
+    def upload_staged(self):
+        """Copy the staged (pinned) batch to its device buffers once; later steps launched with
+        transfers=False then run on that HBM-resident batch."""
+        with torch.cuda.stream(self.stream):
+            self._h2d(self.slot)
+        self.stream.synchronize()
+
+    def set_step_controls(self):
+        """Host side of the per-step control block: dropout seed, scheduled LR, Adam bias correction."""
+        t = self.step_count
+        lam = linear_schedule(t, self.warmup_steps, self.total_steps) if self.total_steps > 0 else 1.0
+        lr = self.lr * lam
+        b1, b2 = self.betas
+        k = t + 1
+        step_size = lr * math.sqrt(1.0 - b2 ** k) / (1.0 - b1 ** k)
+        self.host_hyper[self.slot][0] = lr
+        self.host_hyper[self.slot][1] = step_size
+        self.host_seed[self.slot][0] = int(torch.randint(0, 2 ** 62, (1,), generator=self._gen).item())
+
+    def launch_train_step(self, transfers=True):
+        """Enqueue one training step on the inputs already staged in pinned memory (no host sync).
+        transfers=False replays the variant without the batch H2D / loss D2H copies (inputs resident in
+        HBM): the kernel-only number of bench.py."""
+        self.set_step_controls()
+        slot = self.slot
+        if self.use_graph and not transfers:
+            if self._train_graph_resident is None:
+                saved = (self.eng.flat.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone())
+                self._train_graph_resident = self._capture(lambda: self._train_body(False, slot))
+                self.eng.flat.copy_(saved[0]); self.exp_avg.copy_(saved[1]); self.exp_avg_sq.copy_(saved[2])
+                self.grads.zero_()
+                self.eng.refresh_operands()
+                torch.cuda.synchronize(self.dev)
+            with torch.cuda.stream(self.stream):
+                self._train_graph_resident.replay()
+        elif self.use_graph:
+            if self._train_graph[slot] is None:
+                saved = (self.eng.flat.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone())
+                self._train_graph[slot] = self._capture(lambda: self._train_body(True, slot))
+                # the warm-up run inside _capture applied one optimizer step: undo it
+                self.eng.flat.copy_(saved[0]); self.exp_avg.copy_(saved[1]); self.exp_avg_sq.copy_(saved[2])
+                self.grads.zero_()
+                self.eng.refresh_operands()
+                torch.cuda.synchronize(self.dev)
+            with torch.cuda.stream(self.stream):
+                self._train_graph[slot].replay()
+                self.done[slot].record()
+        else:
+            with torch.cuda.stream(self.stream):
+                self._train_body(transfers, slot)
+                self.done[slot].record()
+        self.step_count += 1
+        self.eng.operands_dirty = False
+        if transfers:
+            self.slot = (slot + 1) % self.NSLOT      # next batch is staged into the other pinned slot
+        return slot
+
+    def submit_train_step(self, input_ids, visual, acoustic, attention_mask=None, token_type_ids=None, labels=None) -> int:
+        """Stage a host batch and enqueue its optimisation step; returns a ticket for `result()`.  Does not
+        wait for the GPU: the next batch can be staged while this step runs."""
+        self._stage(input_ids, visual, acoustic, attention_mask, token_type_ids, labels)
+        return self.launch_train_step()
+
+    def result(self, ticket: int) -> float:
+        """Loss of a submitted step (blocks until that step's D2H copy has landed)."""
+        self.done[ticket].synchronize()
+        return float(self.host_loss[ticket][0])
+
+    def train_step(self, input_ids, visual, acoustic, attention_mask=None, token_type_ids=None, labels=None) -> float:
+        """One optimisation step on a host batch; returns the loss (host float, like `loss.item()`)."""
+        return self.result(self.submit_train_step(input_ids, visual, acoustic, attention_mask, token_type_ids, labels))
+
+    def launch_eval_step(self, transfers=True):
+        slot = self.slot
+        if self.use_graph and not transfers:
+            if self._eval_graph_resident is None:
+                self._eval_graph_resident = self._capture(lambda: self._eval_body(False, slot))
+            with torch.cuda.stream(self.stream):
+                self._eval_graph_resident.replay()
+        elif self.use_graph:
+            if self._eval_graph[slot] is None:
+                self._eval_graph[slot] = self._capture(lambda: self._eval_body(True, slot))
+            with torch.cuda.stream(self.stream):
+                self._eval_graph[slot].replay()
+                self.done[slot].record()
+        else:
+            with torch.cuda.stream(self.stream):
+                self._eval_body(transfers, slot)
+                self.done[slot].record()
+        if transfers:
+            self.slot = (slot + 1) % self.NSLOT
+
+    def eval_step(self, input_ids, visual, acoustic, attention_mask=None, token_type_ids=None) -> torch.Tensor:
+        """Eval-mode logits for a host batch (host tensor [B, num_labels])."""
+        self._stage(input_ids, visual, acoustic, attention_mask, token_type_ids)
+        if self.eng.operands_dirty:
+            self.eng.refresh_operands()
+        self.launch_eval_step()
+        self.stream.synchronize()
+        return self.host_logits.clone()

@@ -40,6 +40,8 @@ extern "C" {
 
 const char* magb200_last_error(void);
 int magb200_version(void);
+/* number of kernels this library has launched (or recorded into a capturing stream) in this process */
+unsigned long long magb200_launch_count(void);
 /* 0 iff the current device is an sm_100 part */
 int magb200_device_check(void);
 
@@ -137,7 +139,10 @@ int magb200_mse_loss(const float* logits, const float* labels, int n, float grad
  * [256 i, 256 i + 256).  Optionally zeroes the gradient and refreshes the fp16 copy p16 in the same pass. */
 int magb200_adamw_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* p16,
                        const uint8_t* decay_chunk, int64_t n, float lr, float beta1, float beta2, float eps,
-                       float weight_decay, int step, float grad_unscale, int zero_grad, void* stream);
+                       float weight_decay, int step, float grad_unscale, int zero_grad, const float* hyper_dev,
+                       void* stream);
+/* hyper_dev (optional, device): {lr, step_size = lr*sqrt(1-b2^t)/(1-b1^t)} read at run time instead of the
+ * by-value lr/step, so a captured CUDA graph follows the LR schedule (multimodal_driver.py:345-350, 384). */
 
 /* ------------------------------------------------------------------------------------------------
  * Whole-model schedules: MAG_BertForSequenceClassification.forward (bert.py:251-324) and the autograd
@@ -170,6 +175,8 @@ typedef struct magb200_bert_dims {
   float p_hidden, p_attn, p_mag, p_cls;               /* dropout probabilities (0 = eval) */
   float grad_scale;                                    /* loss scale carried by every gradient in backward */
   uint64_t seed;                                       /* dropout seed of this step */
+  const uint64_t* seed_dev;                            /* if non-NULL the kernels read the seed from this device word
+                                                          at run time (lets a captured CUDA graph change seed per replay) */
 } magb200_bert_dims;
 
 size_t magb200_bert_workspace_bytes(const magb200_bert_dims* dims);

@@ -1,0 +1,61 @@
+"""CPU, world_size 2 over gloo: the data-parallel recipe of trainer.py / parallel.py (contiguous batch
+shards, local MEAN loss, SUM all-reduce of the flat gradient, 1/world unscale) reproduces the gradient of
+one process on the whole batch.  Local gradients come from the CPU oracle -- the product kernels need a
+GPU; what is under test is the host-side sharding / reduction logic."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    from bert_multimodal_transformer_b200 import parallel
+    from bert_multimodal_transformer_b200.flat import FlatLayout, bert_param_order
+    from oracle import inputs as gen, restatement as R, weights
+    layers = 1
+    sd = {k: v.requires_grad_(True) for k, v in weights.bert_state_dict(num_layers=layers, seed=1).items()}
+    full = gen.bert_batch(4, 16, seed=3)
+    mine = parallel.shard_batch(full, rank, world)
+    assert mine["input_ids"].shape[0] == 2
+    logits = R.mag_bert_forward(sd, mine["input_ids"], mine["visual"], mine["acoustic"], mine["attention_mask"],
+                                mine["token_type_ids"], n_layer=layers)
+    R.mse_loss(logits, mine["labels"]).backward()
+    order = bert_param_order(layers)
+    lay = FlatLayout([(n, tuple(sd[n].shape)) for n in order])
+    flat = torch.zeros(lay.total)
+    for n in order:
+        lay.view(flat, n).copy_(sd[n].grad)
+    parallel.allreduce_sum_(flat)
+    flat.mul_(parallel.grad_unscale(world))
+    if rank == 0:
+        torch.save({n: lay.view(flat, n).clone() for n in order}, os.path.join(out_dir, "dp.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_equals_single_process(tmp_path):
+    from oracle import inputs as gen, restatement as R, weights
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    got = torch.load(os.path.join(str(tmp_path), "dp.pt"))
+    sd = {k: v.requires_grad_(True) for k, v in weights.bert_state_dict(num_layers=1, seed=1).items()}
+    full = gen.bert_batch(4, 16, seed=3)
+    logits = R.mag_bert_forward(sd, full["input_ids"], full["visual"], full["acoustic"], full["attention_mask"],
+                                full["token_type_ids"], n_layer=1)
+    R.mse_loss(logits, full["labels"]).backward()
+    for k, g in got.items():
+        ref = sd[k].grad
+        assert (g - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item()), k
+
+
+def test_shard_slice_contract():
+    from bert_multimodal_transformer_b200.parallel import shard_slice
+    assert shard_slice(128, 3, 8) == slice(48, 64)
+    with pytest.raises(ValueError):
+        shard_slice(50, 0, 8)

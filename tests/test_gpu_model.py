@@ -1,0 +1,206 @@
+"""-m gpu: MAG-BERT through the reference-shaped Python API (which calls the C ABI) against
+(a) the golden vectors minted from the VERBATIM reference and (b) the CPU oracle on the same seeded
+inputs.  North-star tolerance: logits within 1e-3 of the reference."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from bert_multimodal_transformer_b200 import _lib as L
+from oracle import inputs as gen
+from oracle import restatement as R
+from _gpu_util import keep_mask, make_model, rel_err, to_cuda
+
+pytestmark = pytest.mark.gpu
+LOGIT_TOL = 1e-3
+
+
+def _forward(model, cb, **kw):
+    return model(cb["input_ids"], cb["visual"], cb["acoustic"], attention_mask=cb["attention_mask"],
+                 token_type_ids=cb["token_type_ids"], **kw)
+
+
+@pytest.mark.parametrize("name", ["bert_mosi_b8", "bert_mosi_b48", "bert_mosi_b8_reflike", "bert_mosei_b8"])
+def test_logits_match_reference_golden(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    B, V, A, wseed, iseed, reflike = [int(x) for x in g["args"]]
+    model, _ = make_model(12, V, A, wseed, bool(reflike))
+    model.eval()
+    cb = to_cuda(gen.bert_batch(B, 50, V, A, seed=iseed))
+    with torch.no_grad():
+        out = _forward(model, cb)
+        seq, pooled = model.bert(cb["input_ids"], cb["visual"], cb["acoustic"], attention_mask=cb["attention_mask"],
+                                 token_type_ids=cb["token_type_ids"])
+    assert isinstance(out, tuple) and len(out) == 1 and out[0].shape == (B, 1)
+    assert np.abs(out[0].cpu().numpy() - g["logits"]).max() < LOGIT_TOL
+    assert np.abs(pooled.cpu().numpy() - g["pooled"]).max() < 5e-3
+    assert np.abs(seq[:2].cpu().numpy() - g["sequence_output"]).max() < 2e-2
+    eng = model._engine
+    dims, ws = model._last
+    assert np.abs(eng.peek(dims, ws, L.PEEK_EMB)[:2].cpu().numpy() - g["emb"]).max() < 1e-5    # fp32 path, exact
+    assert np.abs(eng.peek(dims, ws, L.PEEK_MAG)[:2].cpu().numpy() - g["mag"]).max() < 5e-3
+
+
+@pytest.mark.parametrize("name", ["bert_mosi_b8", "bert_mosi_b8_reflike"])
+def test_gradients_match_reference_golden(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    B, V, A, wseed, iseed, reflike = [int(x) for x in g["args"]]
+    model, _ = make_model(12, V, A, wseed, bool(reflike))
+    model.eval()   # dropout off: torch's Philox stream cannot be reproduced
+    cb = to_cuda(gen.bert_batch(B, 50, V, A, seed=iseed))
+    out = _forward(model, cb, labels=cb["labels"])
+    assert len(out) == 2 and abs(out[0].item() - float(g["loss"])) < 2e-3
+    out[0].backward()
+    bad = []
+    for k, p in model.named_parameters():
+        ref_norm = float(g["gnorm/" + k])
+        if ref_norm < 1e-7:      # key biases: softmax is shift invariant, the true gradient is 0
+            assert p.grad.norm().item() < 1e-4, k
+            continue
+        if abs(p.grad.norm().item() - ref_norm) > 3e-2 * ref_norm:
+            bad.append((k, p.grad.norm().item(), ref_norm))
+        head = p.grad.flatten()[:8].cpu().numpy()
+        assert np.abs(head - g["ghead/" + k]).max() < 0.05 * max(np.abs(g["ghead/" + k]).max(), ref_norm / p.numel() ** 0.5), k
+    assert not bad, bad[:5]
+
+
+def test_full_gradient_against_oracle_autograd():
+    layers = 3
+    model, sd = make_model(layers, seed=2)
+    model.eval()
+    b = gen.bert_batch(6, 50, seed=5)
+    cb = to_cuda(b)
+    loss = _forward(model, cb, labels=cb["labels"])[0]
+    loss.backward()
+    ref_sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref = R.mag_bert_forward(ref_sd, b["input_ids"], b["visual"], b["acoustic"], b["attention_mask"],
+                             b["token_type_ids"], n_layer=layers)
+    R.mse_loss(ref, b["labels"]).backward()
+    for k, p in model.named_parameters():
+        rg = ref_sd[k].grad
+        if rg.norm().item() < 1e-7:
+            continue
+        assert rel_err(p.grad, rg) < 3e-2, (k, rel_err(p.grad, rg))
+
+
+def test_training_mode_matches_oracle_with_the_kernels_dropout_masks():
+    """Dropout on: the oracle is fed the exact keep-masks libmagb200 generates (counter RNG), so the
+    training-mode forward and gradients can be compared too."""
+    layers, B, S = 2, 4, 50
+    model, sd = make_model(layers, seed=6)
+    model.train()
+    b = gen.bert_batch(B, S, seed=9)
+    cb = to_cuda(b)
+    torch.manual_seed(77)
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    torch.manual_seed(77)
+    loss = _forward(model, cb, labels=cb["labels"])[0]
+    loss.backward()
+    sites = {"emb": (1, (B, S, 768), 0.1), "mag": (2, (B, S, 768), 0.5), "pooled": (3, (B, 768), 0.1)}
+    for l in range(layers):
+        sites[f"L{l}.attn_prob"] = (16 + 4 * l, (B, 12, S, S), 0.1)
+        sites[f"L{l}.attn_out"] = (17 + 4 * l, (B, S, 768), 0.1)
+        sites[f"L{l}.ffn_out"] = (18 + 4 * l, (B, S, 768), 0.1)
+    masks = {k: (keep_mask(shape, p, seed, site).cpu(), p) for k, (site, shape, p) in sites.items()}
+
+    def drop(site, x):
+        m, p = masks[site]
+        return x * m / (1 - p)
+
+    ref_sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref = R.mag_bert_forward(ref_sd, b["input_ids"], b["visual"], b["acoustic"], b["attention_mask"],
+                             b["token_type_ids"], n_layer=layers, drop=drop)
+    ref_loss = R.mse_loss(ref, b["labels"])
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) < 5e-3
+    for k in ("classifier.weight", "bert.encoder.layer.1.output.dense.weight", "bert.encoder.layer.0.attention.self.query.weight",
+              "bert.MAG.W_hv.weight", "bert.embeddings.LayerNorm.weight", "bert.embeddings.position_embeddings.weight"):
+        p = dict(model.named_parameters())[k]
+        assert rel_err(p.grad, ref_sd[k].grad) < 4e-2, (k, rel_err(p.grad, ref_sd[k].grad))
+
+
+def test_full_size_properties():
+    """BASELINE.json configs[1] size (bs=48): size-independent properties.
+    (1) samples are independent -> permuting the batch permutes the logits, bit for bit;
+    (2) padded positions cannot influence the CLS output -> logits are bit-identical when pad tokens /
+        modality rows change (masked keys get exp(-10000 + ...) == 0 exactly)."""
+    model, _ = make_model(12, seed=0)
+    model.eval()
+    b = gen.bert_batch(48, 50, seed=1234)
+    cb = to_cuda(b)
+    with torch.no_grad():
+        base = _forward(model, cb)[0]
+        perm = torch.randperm(48, generator=torch.Generator().manual_seed(0)).cuda()
+        pb = {k: v[perm] for k, v in cb.items()}
+        assert torch.equal(_forward(model, pb)[0], base[perm])
+        noisy = {k: v.clone() for k, v in cb.items()}
+        pad = cb["attention_mask"] == 0
+        noisy["input_ids"][pad] = 1999
+        noisy["visual"][pad] = 3.0
+        noisy["acoustic"][pad] = -2.0
+        assert torch.equal(_forward(model, noisy)[0], base)
+
+
+def test_api_contract_and_errors():
+    model, _ = make_model(1, seed=1)
+    model.eval()
+    cb = to_cuda(gen.bert_batch(2, 50, seed=3))
+    with pytest.raises(ValueError, match="You have to specify either input_ids or inputs_embeds"):
+        model(None, cb["visual"], cb["acoustic"])
+    with pytest.raises(ValueError, match="cannot specify both"):
+        model(cb["input_ids"], cb["visual"], cb["acoustic"], inputs_embeds=torch.zeros(2, 50, 768))
+    with pytest.raises(NotImplementedError):
+        model(cb["input_ids"], cb["visual"], cb["acoustic"], output_attentions=True)
+    with torch.no_grad():
+        a = model(cb["input_ids"], cb["visual"], cb["acoustic"])[0]                       # default mask / segments
+        ones = torch.ones_like(cb["input_ids"])
+        b = model(cb["input_ids"], cb["visual"], cb["acoustic"], ones, torch.zeros_like(ones))[0]   # positional order
+    assert torch.equal(a, b)
+    # parameters keep the reference's names and weight-decay grouping works (multimodal_driver.py:328-343)
+    names = [n for n, _ in model.named_parameters()]
+    assert "bert.MAG.W_hv.weight" in names and "classifier.bias" in names
+    assert len(names) == 5 + 16 * 1 + 2 + 10 + 2
+
+
+def test_external_optimizer_updates_are_seen_by_the_next_forward():
+    """multimodal_driver.py:383-386: an external optimizer mutates p.data in place between calls."""
+    model, _ = make_model(1, seed=1)
+    model.train()
+    cb = to_cuda(gen.bert_batch(4, 50, seed=3))
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-2)
+    model.eval()
+    with torch.no_grad():
+        before = _forward(model, cb)[0].clone()
+    model.train()
+    loss = _forward(model, cb, labels=cb["labels"])[0]
+    loss.backward()
+    opt.step()
+    model.eval()
+    with torch.no_grad():
+        after = _forward(model, cb)[0]
+    assert (after - before).abs().max().item() > 1e-3
+
+
+def test_trainer_graph_step_equals_eager_step_and_learns():
+    from bert_multimodal_transformer_b200.trainer import MagBertTrainer
+    b = gen.bert_batch(8, 50, seed=21)
+    labels = b["labels"]
+    losses, finals, start = {}, {}, {}
+    for graph in (False, True):
+        model, _ = make_model(2, seed=4)
+        model.train()
+        tr = MagBertTrainer(model, 8, 50, lr=2e-4, total_steps=0, use_cuda_graph=graph, seed=5)
+        args = (b["input_ids"], b["visual"], b["acoustic"], b["attention_mask"], b["token_type_ids"])
+        start[graph] = torch.nn.functional.mse_loss(tr.eval_step(*args).view(-1), labels).item()
+        losses[graph] = [tr.train_step(*args, labels) for _ in range(12)]
+        finals[graph] = tr.eval_step(*args).clone()
+        model.eval()
+        with torch.no_grad():
+            direct = _forward(model, to_cuda(b))[0].cpu()
+        assert (direct - finals[graph]).abs().max().item() < 1e-5      # trainer and module API share the weights
+        end = torch.nn.functional.mse_loss(finals[graph].view(-1), labels).item()
+        assert end < 0.7 * start[graph], (start[graph], end)            # it learns (eval-mode loss on the batch)
+    # same seeds, same kernels: graph replay and eager launches agree (up to fp32 atomic ordering)
+    assert abs(start[False] - start[True]) < 1e-6
+    assert abs(losses[False][0] - losses[True][0]) < 1e-4 and abs(losses[False][1] - losses[True][1]) < 1e-3
