@@ -322,6 +322,11 @@ def run_gpu_arm(args):
         ms = float(t.item())
     value = world * BS * args.steps / (ms * 1e-3)
     loss_after = float(trainer.loss.item())
+    if args.profile_mode:
+        if rank == 0:
+            print(json.dumps({"profile_mode": True, "value_under_profiler": value, "ms_per_step": ms / args.steps,
+                              "gpu_launches_per_step": int(launches_per_step)}), flush=True)
+        return
 
     # ---------------- e2e: host batch -> pinned -> H2D -> step -> loss D2H, every step, through train_step()
     for _ in range(3):
@@ -438,6 +443,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-mode", action="store_true",
+                    help="only run the warm-up + timed train steps (for ncu captures); prints a reduced line")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -45,6 +45,7 @@ SIGNATURES = {
     "magb200_version": (c_int, []),
     "magb200_launch_count": (c_uint64, []),
     "magb200_device_check": (c_int, []),
+    "magb200_gemm_set_debug": (None, [c_void_p, c_int]),
     "magb200_gemm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                              c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_int, c_int, c_int,
                              c_void_p]),
@@ -64,9 +65,9 @@ SIGNATURES = {
     "magb200_ln_bwd": (c_int, [c_void_p] * 5 + [c_float, c_uint64, c_uint32, c_int, c_float] + [c_void_p] * 6),
     "magb200_colsum_f16": (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p]),
     "magb200_sdpa_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_uint64, c_uint32, c_void_p,
-                                 c_void_p]),
-    "magb200_sdpa_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_uint64, c_uint32,
                                  c_void_p, c_void_p]),
+    "magb200_sdpa_bwd": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_int, c_float, c_uint64, c_uint32, c_float,
+                                                  c_void_p, c_void_p, c_void_p]),
     "magb200_cls_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_uint64, c_uint32, c_void_p,
                                 c_void_p, c_void_p]),
     "magb200_cls_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_uint64, c_uint32, c_float,

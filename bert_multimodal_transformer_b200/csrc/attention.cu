@@ -257,9 +257,11 @@ static int launch_fwd(const __half* qkv, const int64_t* mask, int B, int S, int 
 }
 
 int sdpa_fwd(const __half* qkv, const int64_t* mask, int B, int S, int heads, int head_dim, float p, Seed seed,
-             uint32_t site, __half* ctx, cudaStream_t st) {
+             uint32_t site, __half* ctx, float* lse, cudaStream_t st) {
   MAGB_REQUIRE(head_dim == DH, "sdpa: head_dim must be 64");
   MAGB_REQUIRE(S >= 1 && S <= 512, "sdpa: sequence length %d out of range [1,512]", S);
+  // short sequences with an lse buffer: warp-MMA kernel (attention_mma.cu); otherwise the general kernel
+  if (S <= 64 && lse != nullptr) return sdpa_fwd_mma(qkv, mask, B, S, heads, p, seed, site, ctx, lse, st);
   if (S <= 64) return launch_fwd<2>(qkv, mask, B, S, heads, p, seed, site, ctx, st);
   if (S <= 128) return launch_fwd<4>(qkv, mask, B, S, heads, p, seed, site, ctx, st);
   if (S <= 256) return launch_fwd<8>(qkv, mask, B, S, heads, p, seed, site, ctx, st);
@@ -285,12 +287,18 @@ static int launch_bwd(const __half* qkv, const __half* dctx, const int64_t* mask
   return 0;
 }
 
-int sdpa_bwd(const __half* qkv, const __half* dctx, const int64_t* mask, int B, int S, int heads, int head_dim,
-             float p, Seed seed, uint32_t site, __half* dqkv, cudaStream_t st) {
+int sdpa_bwd(const __half* qkv, const __half* dctx, const __half* ctx, const float* lse, const int64_t* mask, int B,
+             int S, int heads, int head_dim, float p, Seed seed, uint32_t site, float oscale, __half* dqkv, float* dbias,
+             cudaStream_t st) {
   MAGB_REQUIRE(head_dim == DH, "sdpa: head_dim must be 64");
   MAGB_REQUIRE(S >= 1 && S <= 128, "sdpa backward: sequence length %d out of range [1,128] (materialises S x S)", S);
-  if (S <= 64) return launch_bwd<2>(qkv, dctx, mask, B, S, heads, p, seed, site, dqkv, st);
-  return launch_bwd<4>(qkv, dctx, mask, B, S, heads, p, seed, site, dqkv, st);
+  if (S <= 64 && lse != nullptr && ctx != nullptr)
+    return sdpa_bwd_mma(qkv, dctx, ctx, lse, mask, B, S, heads, p, seed, site, oscale, dqkv, dbias, st);
+  int rc = S <= 64 ? launch_bwd<2>(qkv, dctx, mask, B, S, heads, p, seed, site, dqkv, st)
+                   : launch_bwd<4>(qkv, dctx, mask, B, S, heads, p, seed, site, dqkv, st);
+  if (rc) return rc;
+  if (dbias != nullptr) return colsum_f16(dqkv, B * S, 3 * heads * DH, oscale, dbias, st);
+  return 0;
 }
 
 }  // namespace magb200

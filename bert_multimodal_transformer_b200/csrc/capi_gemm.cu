@@ -39,6 +39,10 @@ int magb200_device_check(void) {
   return 0;
 }
 
+void magb200_gemm_set_debug(void* trace_dev, int cfg) {
+  gemm_set_debug(reinterpret_cast<unsigned long long*>(trace_dev), cfg);
+}
+
 int magb200_gemm(const void* A, const void* B, int M, int N, int K, int lda, int ldb, int a_dtype, int b_dtype,
                  int a_mn_major, int b_mn_major, int epilogue, const float* bias, void* out0, void* out1,
                  const void* aux, int ldo, float alpha, int splits, int n_split, int k_start_hi, void* stream) {

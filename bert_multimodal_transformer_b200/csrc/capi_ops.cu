@@ -105,15 +105,17 @@ int magb200_colsum_f16(const void* in_f16, int T, int N, float out_scale, float*
 }
 
 int magb200_sdpa_fwd(const void* qkv16, const int64_t* mask, int B, int S, int heads, int head_dim, float p,
-                     uint64_t seed, uint32_t site, void* ctx16, void* stream) {
+                     uint64_t seed, uint32_t site, void* ctx16, float* lse, void* stream) {
   return sdpa_fwd(reinterpret_cast<const __half*>(qkv16), mask, B, S, heads, head_dim, p, Seed{seed, nullptr}, site,
-                  reinterpret_cast<__half*>(ctx16), ST);
+                  reinterpret_cast<__half*>(ctx16), lse, ST);
 }
 
-int magb200_sdpa_bwd(const void* qkv16, const void* dctx16, const int64_t* mask, int B, int S, int heads, int head_dim,
-                     float p, uint64_t seed, uint32_t site, void* dqkv16, void* stream) {
-  return sdpa_bwd(reinterpret_cast<const __half*>(qkv16), reinterpret_cast<const __half*>(dctx16), mask, B, S, heads,
-                  head_dim, p, Seed{seed, nullptr}, site, reinterpret_cast<__half*>(dqkv16), ST);
+int magb200_sdpa_bwd(const void* qkv16, const void* dctx16, const void* ctx16, const float* lse, const int64_t* mask,
+                     int B, int S, int heads, int head_dim, float p, uint64_t seed, uint32_t site, float out_scale,
+                     void* dqkv16, float* dbias, void* stream) {
+  return sdpa_bwd(reinterpret_cast<const __half*>(qkv16), reinterpret_cast<const __half*>(dctx16),
+                  reinterpret_cast<const __half*>(ctx16), lse, mask, B, S, heads, head_dim, p, Seed{seed, nullptr}, site,
+                  out_scale, reinterpret_cast<__half*>(dqkv16), dbias, ST);
 }
 
 int magb200_cls_fwd(const float* pre, const float* Wc, const float* bc, int B, int num_labels, float p, uint64_t seed,

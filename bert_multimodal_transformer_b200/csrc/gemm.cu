@@ -110,6 +110,11 @@ static int launch_majors(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUte
   return launch_variant<EB, true, true, BN, STAGES>(ta, tb, g, grid, st);
 }
 
+// debug/tuning hooks (tools/gemm_tune.py): trace buffer and tile-configuration override
+static unsigned long long* g_trace = nullptr;
+static int g_cfg = 0;
+void gemm_set_debug(unsigned long long* trace, int cfg) { g_trace = trace; g_cfg = cfg; }
+
 int gemm_launch(const GemmProblem& p, cudaStream_t st) {
   MAGB_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem %dx%dx%d", p.M, p.N, p.K);
   const bool a32 = p.a_dtype == DT_F32, b32 = p.b_dtype == DT_F32;
@@ -119,7 +124,7 @@ int gemm_launch(const GemmProblem& p, cudaStream_t st) {
   MAGB_REQUIRE(!(a32 && (p.a_mn || p.b_mn)), "gemm: tf32 operands must be K-major");
   const int EB = a32 ? 4 : 2;
   const int BK = 128 / EB, ATOM = 128 / EB, BM = 128;
-  const int BN = 128;
+  const int BN = (g_cfg >= 3) ? 256 : 128;
   MAGB_REQUIRE(p.N % 32 == 0, "gemm: N=%d must be a multiple of 32", p.N);
   MAGB_REQUIRE(p.ldo % 8 == 0, "gemm: ldo=%d must be a multiple of 8", p.ldo);
 
@@ -141,6 +146,7 @@ int gemm_launch(const GemmProblem& p, cudaStream_t st) {
   splits = (g.kb_total + g.kb_per_split - 1) / g.kb_per_split;  // no empty split
   MAGB_REQUIRE(splits == 1 || p.epi == EPI_ATOMIC_F32, "gemm: split-K requires the atomic epilogue");
   g.n_split = p.n_split > 0 ? p.n_split : 0x7fffffff;
+  MAGB_REQUIRE(p.n_split <= 0 || p.n_split % BN == 0, "gemm: n_split must be a multiple of the N tile");
   g.kb_start_hi = p.k_start_hi / BK;
   MAGB_REQUIRE(p.k_start_hi % BK == 0, "gemm: k_start_hi must be a multiple of the K block");
   MAGB_REQUIRE(p.n_split <= 0 || (splits == 1 && g.kb_start_hi < g.kb_total && p.n_split % BN == 0),
@@ -149,9 +155,18 @@ int gemm_launch(const GemmProblem& p, cudaStream_t st) {
   const uint32_t af = p.a_dtype == DT_F32 ? 2u : (p.a_dtype == DT_BF16 ? 1u : 0u);
   const uint32_t bf = p.b_dtype == DT_F32 ? 2u : (p.b_dtype == DT_BF16 ? 1u : 0u);
   g.idesc = make_idesc(af, bf, p.a_mn, p.b_mn, BM, BN);
+  g.trace = g_trace;
 
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, splits);
-  if (EB == 2) return launch_majors<2, 128, 3>(p.a_mn, p.b_mn, ta, tb, g, grid, st);
+  if (EB == 2) {
+    switch (g_cfg) {
+      case 1: return launch_majors<2, 128, 4>(p.a_mn, p.b_mn, ta, tb, g, grid, st);
+      case 2: return launch_majors<2, 128, 6>(p.a_mn, p.b_mn, ta, tb, g, grid, st);
+      case 3: return launch_majors<2, 256, 3>(p.a_mn, p.b_mn, ta, tb, g, grid, st);
+      case 4: return launch_majors<2, 256, 4>(p.a_mn, p.b_mn, ta, tb, g, grid, st);
+      default: return launch_majors<2, 128, 3>(p.a_mn, p.b_mn, ta, tb, g, grid, st);
+    }
+  }
   return launch_majors<4, 128, 3>(p.a_mn, p.b_mn, ta, tb, g, grid, st);
 }
 

@@ -45,6 +45,7 @@ struct GemmArgs {
   int ldo;            // leading dimension (elements) of out0/out1/aux
   float alpha;
   uint32_t idesc;
+  unsigned long long* trace;   // debug: per-CTA clock64 stamps (64 slots per CTA) or null
 };
 
 template <int EB>
@@ -72,9 +73,55 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// One thread owns 32 consecutive columns [n, n+32) of output row m.
-__device__ __forceinline__ void gemm_epilogue_row32(const GemmArgs& g, int m, int n, uint32_t (&r)[32]) {
-  float v[32];
+// ------------------------------------------------------------------------------------------------
+// Epilogue.  tcgen05.ld (32x32b) hands thread i of a warp row (lane base + i) of the accumulator, 32
+// consecutive columns at a time.  Writing that straight to global memory makes every store
+// instruction touch 32 different rows (measured: 5.5k cycles for a 128x128 fp32 tile, as long as the
+// whole K=768 main loop).  Instead each epilogue warp owns a [32 rows][BN cols] staging tile in the
+// (now idle) pipeline shared memory: threads write their row into it, then the warp copies whole rows
+// out with fully coalesced 16-byte accesses (512 B contiguous per instruction).  Auxiliary inputs
+// (residual to add, pre-GELU activations) take the same path in reverse.
+template <int BN>
+struct EpiStage {
+  static constexpr int PITCH = BN * 4 + 16;        // bytes per staged row (fp32 worst case + bank skew)
+  static constexpr int WARP_BYTES = 32 * PITCH;
+};
+
+// global [rows][rowbytes] (pitch gpitch bytes) -> staging, coalesced
+__device__ __forceinline__ void stage_in(uint8_t* stg, int pitch, const uint8_t* __restrict__ gsrc, size_t gpitch,
+                                         int rows, int rowbytes, int lane) {
+  const int lpr = rowbytes >> 4;                   // lanes per row (16 B each): 8, 16, 32 or 64
+  if (lpr <= 32) {
+    const int rpi = 32 / lpr;                      // rows per instruction
+    const int lr = lane / lpr, lc = (lane % lpr) << 4;
+    for (int r = lr; r < rows; r += rpi)
+      *reinterpret_cast<uint4*>(stg + r * pitch + lc) = *reinterpret_cast<const uint4*>(gsrc + (size_t)r * gpitch + lc);
+  } else {
+    for (int r = 0; r < rows; ++r)
+      for (int c = lane << 4; c < rowbytes; c += 512)
+        *reinterpret_cast<uint4*>(stg + r * pitch + c) = *reinterpret_cast<const uint4*>(gsrc + (size_t)r * gpitch + c);
+  }
+}
+// staging -> global, coalesced store (or fp32 reduction when `atomic`)
+__device__ __forceinline__ void stage_out(const uint8_t* stg, int pitch, uint8_t* __restrict__ gdst, size_t gpitch,
+                                          int rows, int rowbytes, int lane, bool atomic) {
+  const int lpr = rowbytes >> 4;
+  const int rpi = lpr <= 32 ? 32 / lpr : 1;
+  const int lr = lpr <= 32 ? lane / lpr : 0;
+  const int lc0 = lpr <= 32 ? (lane % lpr) << 4 : lane << 4;
+  for (int r = lr; r < rows; r += rpi) {
+    for (int c = lc0; c < rowbytes; c += 512) {
+      const uint4 v = *reinterpret_cast<const uint4*>(stg + r * pitch + c);
+      uint8_t* d = gdst + (size_t)r * gpitch + c;
+      if (!atomic) st_global_v4(d, v.x, v.y, v.z, v.w);
+      else red_add_v4(reinterpret_cast<float*>(d), __uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z),
+                      __uint_as_float(v.w));
+    }
+  }
+}
+
+// acc[32] (this thread's row, columns [n, n+32)) -> v = alpha * acc + bias
+__device__ __forceinline__ void epi_affine(const GemmArgs& g, int n, const uint32_t (&r)[32], float (&v)[32]) {
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * g.alpha;
   if (g.bias != nullptr) {
@@ -85,91 +132,121 @@ __device__ __forceinline__ void gemm_epilogue_row32(const GemmArgs& g, int m, in
       v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
     }
   }
-  const size_t off = (size_t)m * g.ldo + n;
-  switch (g.epi) {
-    case EPI_STORE_F32:
-    case EPI_RELU_F32:
-    case EPI_STORE_F32_F16: {
-      if (g.epi == EPI_RELU_F32) {
+}
+__device__ __forceinline__ void row_write_f32(uint8_t* row, int c, const float (&v)[32]) {
+  float4* d = reinterpret_cast<float4*>(row + c * 128);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  for (int j = 0; j < 8; ++j) d[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+template <bool BF16>
+__device__ __forceinline__ void row_write_16(uint8_t* row, int c, const float (&v)[32]) {
+  uint4* d = reinterpret_cast<uint4*>(row + c * 64);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (BF16) d[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+    else d[j] = make_uint4(pack_f16(v[8 * j], v[8 * j + 1]), pack_f16(v[8 * j + 2], v[8 * j + 3]),
+                           pack_f16(v[8 * j + 4], v[8 * j + 5]), pack_f16(v[8 * j + 6], v[8 * j + 7]));
+  }
+}
+
+// One epilogue warp: rows [m_base, m_base+32) x columns [n0, n0+BN) of the output.
+template <int BN>
+__device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& g, uint32_t tmem_warp, int m_base, int n0,
+                                                   uint8_t* stg, int lane, unsigned long long* tr) {
+  constexpr int PITCH = EpiStage<BN>::PITCH;
+  const int rows = min(32, g.M - m_base);                   // may be <= 0 for a tail tile
+  const int ncols = min(BN, g.N - n0);                      // multiple of 32
+  const bool live = rows > 0 && ncols > 0;
+  uint8_t* myrow = stg + lane * PITCH;
+  const int epi = g.epi;
+  // -------- auxiliary input through the staging tile (coalesced)
+  const bool aux32 = (epi == EPI_STORE_F32) && g.aux != nullptr;
+  const bool aux16 = (epi == EPI_DGELU_F16);
+  if (live && (aux32 || aux16)) {
+    const int es = aux32 ? 4 : 2;
+    stage_in(stg, PITCH, reinterpret_cast<const uint8_t*>(g.aux) + ((size_t)m_base * g.ldo + n0) * es,
+             (size_t)g.ldo * es, rows, ncols * es, lane);
+  }
+  __syncwarp();
+  const int npass = (epi == EPI_GELU_F16 && g.out1 != nullptr) || epi == EPI_STORE_F32_F16 ? 2 : 1;
+  for (int pass = 0; pass < npass; ++pass) {
+    // which output this pass produces, and its element size
+    int es = 4;
+    void* out = g.out0;
+    if (epi == EPI_STORE_F16 || epi == EPI_STORE_BF16 || epi == EPI_DGELU_F16) es = 2;
+    if (epi == EPI_GELU_F16) { es = 2; out = (npass == 2 && pass == 0) ? g.out1 : g.out0; }
+    if (epi == EPI_STORE_F32_F16) { es = pass == 0 ? 4 : 2; out = pass == 0 ? g.out0 : g.out1; }
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_warp + (uint32_t)(c * 32), r);      // warp-collective: executed by every lane
+      tmem_ld_wait();
+      if (tr && c < 4) tr[52 + c] = clock64();
+      if (!live || c * 32 >= ncols) continue;
+      float v[32];
+      epi_affine(g, n0 + c * 32, r, v);
+      switch (epi) {
+        case EPI_STORE_F32:
+          if (aux32) {
+            const float4* a4 = reinterpret_cast<const float4*>(myrow + c * 128);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 a = a4[j];
+              v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+            }
+          }
+          row_write_f32(myrow, c, v);
+          break;
+        case EPI_ATOMIC_F32:
+          row_write_f32(myrow, c, v);
+          break;
+        case EPI_RELU_F32:
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          row_write_f32(myrow, c, v);
+          break;
+        case EPI_STORE_F32_F16:
+          if (pass == 0) row_write_f32(myrow, c, v);
+          else row_write_16<false>(myrow, c, v);
+          break;
+        case EPI_STORE_F16:
+          row_write_16<false>(myrow, c, v);
+          break;
+        case EPI_STORE_BF16:
+          row_write_16<true>(myrow, c, v);
+          break;
+        case EPI_GELU_F16:
+          if (!(npass == 2 && pass == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          }
+          row_write_16<false>(myrow, c, v);
+          break;
+        case EPI_DGELU_F16: {
+          const uint4* u4 = reinterpret_cast<const uint4*>(myrow + c * 64);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 u = u4[j];
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[t]));
+              v[8 * j + 2 * t] *= gelu_erf_grad(f.x);
+              v[8 * j + 2 * t + 1] *= gelu_erf_grad(f.y);
+            }
+          }
+          row_write_16<false>(myrow, c, v);
+        } break;
+        default: break;
       }
-      if (g.aux != nullptr && g.epi == EPI_STORE_F32) {
-        const float4* a4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g.aux) + off);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 a = a4[j];
-          v[4 * j + 0] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
-        }
-      }
-      float* o = reinterpret_cast<float*>(g.out0) + off;
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        st_global_v4(o + 4 * j, __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
-                     __float_as_uint(v[4 * j + 3]));
-      if (g.epi == EPI_STORE_F32_F16) {
-        __half* o1 = reinterpret_cast<__half*>(g.out1) + off;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          st_global_v4(o1 + 8 * j, pack_f16(v[8 * j], v[8 * j + 1]), pack_f16(v[8 * j + 2], v[8 * j + 3]),
-                       pack_f16(v[8 * j + 4], v[8 * j + 5]), pack_f16(v[8 * j + 6], v[8 * j + 7]));
-      }
-    } break;
-    case EPI_STORE_F16: {
-      __half* o = reinterpret_cast<__half*>(g.out0) + off;
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        st_global_v4(o + 8 * j, pack_f16(v[8 * j], v[8 * j + 1]), pack_f16(v[8 * j + 2], v[8 * j + 3]),
-                     pack_f16(v[8 * j + 4], v[8 * j + 5]), pack_f16(v[8 * j + 6], v[8 * j + 7]));
-    } break;
-    case EPI_STORE_BF16: {
-      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(g.out0) + off;
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        st_global_v4(o + 8 * j, pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                     pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-    } break;
-    case EPI_GELU_F16: {
-      if (g.out1 != nullptr) {
-        __half* o1 = reinterpret_cast<__half*>(g.out1) + off;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          st_global_v4(o1 + 8 * j, pack_f16(v[8 * j], v[8 * j + 1]), pack_f16(v[8 * j + 2], v[8 * j + 3]),
-                       pack_f16(v[8 * j + 4], v[8 * j + 5]), pack_f16(v[8 * j + 6], v[8 * j + 7]));
-      }
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-      __half* o = reinterpret_cast<__half*>(g.out0) + off;
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        st_global_v4(o + 8 * j, pack_f16(v[8 * j], v[8 * j + 1]), pack_f16(v[8 * j + 2], v[8 * j + 3]),
-                     pack_f16(v[8 * j + 4], v[8 * j + 5]), pack_f16(v[8 * j + 6], v[8 * j + 7]));
-    } break;
-    case EPI_DGELU_F16: {
-      const uint4* u4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(g.aux) + off);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint4 u = u4[j];
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[t]));
-          v[8 * j + 2 * t] *= gelu_erf_grad(f.x);
-          v[8 * j + 2 * t + 1] *= gelu_erf_grad(f.y);
-        }
-      }
-      __half* o = reinterpret_cast<__half*>(g.out0) + off;
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        st_global_v4(o + 8 * j, pack_f16(v[8 * j], v[8 * j + 1]), pack_f16(v[8 * j + 2], v[8 * j + 3]),
-                     pack_f16(v[8 * j + 4], v[8 * j + 5]), pack_f16(v[8 * j + 6], v[8 * j + 7]));
-    } break;
-    case EPI_ATOMIC_F32: {
-      float* o = reinterpret_cast<float*>(g.out0) + off;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) red_add_v4(o + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    } break;
-    default: break;
+    }
+    __syncwarp();
+    if (tr) tr[56] = clock64();
+    if (live)
+      stage_out(stg, PITCH, reinterpret_cast<uint8_t*>(out) + ((size_t)m_base * g.ldo + n0) * es, (size_t)g.ldo * es,
+                rows, ncols * es, lane, epi == EPI_ATOMIC_F32);
+    __syncwarp();
   }
 }
 
@@ -200,6 +277,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  unsigned long long* tr = g.trace ? g.trace + 64ull * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) : nullptr;
+  if (tr && threadIdx.x == 0) tr[0] = clock64();
   const int n0 = blockIdx.x * BN;
   const int m0 = blockIdx.y * T::BM;
 
@@ -229,6 +308,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tr && threadIdx.x == 0) tr[1] = clock64();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -255,6 +335,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int i = 0; i < BN / T::ATOM; ++i)
             tma_load_2d(b_dst + i * (T::BK * 128), &tmB, &full_bar[s], n0 + i * T::ATOM, k0);
         }
+        if (tr && it < 16) tr[2 + it] = clock64();
       }
     }
   } else if (warp == 1) {
@@ -265,6 +346,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
+        if (tr && it < 16) tr[20 + it] = clock64();
         const uint32_t a_base = smem_u32(smem + s * SM::STAGE_BYTES);
         const uint32_t b_base = a_base + SM::A_BYTES;
 #pragma unroll
@@ -280,6 +362,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           else tc_mma_tf32(tmem_base, adesc, bdesc, g.idesc, (it | k) != 0);
         }
         tc_commit(&empty_bar[s]);  // smem slot reusable once these MMAs have read it
+        if (tr && it < 16) tr[40 + it] = clock64();
       }
       tc_commit(tmem_full_bar);    // accumulator complete
     }
@@ -287,20 +370,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    if (tr && threadIdx.x == 64) tr[60] = clock64();
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int m = m0 + q * 32 + lane;
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-      tmem_ld_wait();
-      const int n = n0 + c * 32;
-      if (m < g.M && n < g.N) gemm_epilogue_row32(g, m, n, r);
-    }
+    // the accumulator is complete => every TMA load has landed and every MMA has read its operands:
+    // the pipeline stages are idle and serve as this warp's staging tile
+    static_assert(4 * EpiStage<BN>::WARP_BYTES <= STAGES * SM::STAGE_BYTES, "staging does not fit in the pipeline smem");
+    gemm_epilogue_warp<BN>(g, tmem_base + ((uint32_t)(q * 32) << 16), m0 + q * 32, n0,
+                           smem + q * EpiStage<BN>::WARP_BYTES, lane, threadIdx.x == 64 ? tr : nullptr);
+    if (tr && threadIdx.x == 64) tr[61] = clock64();
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, BN);
+  if (tr && threadIdx.x == 0) tr[62] = clock64();
 }
 
 #endif  // __CUDACC__

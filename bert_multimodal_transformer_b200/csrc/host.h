@@ -34,6 +34,7 @@ struct GemmProblem {
 };
 
 int gemm_launch(const GemmProblem& p, cudaStream_t stream);
+void gemm_set_debug(unsigned long long* trace, int cfg);
 
 // ---------------------------------------------------------------- rowops.cu
 struct EmbedArgs {
@@ -74,10 +75,18 @@ int dropout_mask(uint8_t* out, int64_t n, float p, Seed seed, uint32_t site, cud
 
 
 // ---------------------------------------------------------------- attention.cu
+// lse (fwd out / bwd in, [B][heads][S] fp32) and ctx select the warp-MMA kernels for S <= 64; dbias (nullable)
+// receives oscale * column sums of dqkv (the fused q|k|v bias gradient)
 int sdpa_fwd(const __half* qkv, const int64_t* mask, int B, int S, int heads, int head_dim, float p, Seed seed,
-             uint32_t site, __half* ctx, cudaStream_t st);
-int sdpa_bwd(const __half* qkv, const __half* dctx, const int64_t* mask, int B, int S, int heads, int head_dim, float p,
-             Seed seed, uint32_t site, __half* dqkv, cudaStream_t st);
+             uint32_t site, __half* ctx, float* lse, cudaStream_t st);
+int sdpa_bwd(const __half* qkv, const __half* dctx, const __half* ctx, const float* lse, const int64_t* mask, int B,
+             int S, int heads, int head_dim, float p, Seed seed, uint32_t site, float oscale, __half* dqkv, float* dbias,
+             cudaStream_t st);
+int sdpa_fwd_mma(const __half* qkv, const int64_t* mask, int B, int S, int heads, float p, Seed seed, uint32_t site,
+                 __half* ctx, float* lse, cudaStream_t st);
+int sdpa_bwd_mma(const __half* qkv, const __half* dctx, const __half* ctx, const float* lse, const int64_t* mask, int B,
+                 int S, int heads, float p, Seed seed, uint32_t site, float oscale, __half* dqkv, float* dbias,
+                 cudaStream_t st);
 
 // ---------------------------------------------------------------- head_optim.cu
 int cls_fwd(const float* pre, const float* Wc, const float* bc, int B, int L, float p, Seed seed, uint32_t site,

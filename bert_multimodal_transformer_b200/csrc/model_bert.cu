@@ -32,6 +32,7 @@ struct Carve {
 
 struct LayerWs {
   __half* qkv16; __half* ctx16; float* a32; __half* a16; __half* u16; __half* g16; float* rstd1; float* rstd2;
+  float* lse;
 };
 
 struct BertWs {
@@ -67,6 +68,7 @@ BertWs carve_ws(const magb200_bert_dims& d, void* base) {
     L.g16 = c.take<__half>(T * I);
     L.rstd1 = c.take<float>(T);
     L.rstd2 = c.take<float>(T);
+    L.lse = c.take<float>((size_t)d.batch * d.heads * d.seq);
   }
   w.pre32 = c.take<float>(T * H);
   w.poolpre32 = c.take<float>((size_t)d.batch * H);
@@ -178,7 +180,7 @@ int bert_forward(const magb200_bert_dims& d, const int64_t* off, const float* P,
     LayerWs& L = w.layer[l];
     RUN(linear_fwd(w.x16[l], H, P16 + o[MAGB200_LOFF_QKV_W], T, 3 * H, H, P + o[MAGB200_LOFF_QKV_B], EPI_STORE_F16,
                    L.qkv16, nullptr, 3 * H, st));
-    RUN(sdpa_fwd(L.qkv16, mask, B, S, d.heads, H / d.heads, d.p_attn, sd, site_attn_prob(l), L.ctx16, st));
+    RUN(sdpa_fwd(L.qkv16, mask, B, S, d.heads, H / d.heads, d.p_attn, sd, site_attn_prob(l), L.ctx16, L.lse, st));
     RUN(linear_fwd(L.ctx16, H, P16 + o[MAGB200_LOFF_AO_W], T, H, H, P + o[MAGB200_LOFF_AO_B], EPI_STORE_F32, w.pre32,
                    nullptr, H, st));
     RUN(dropout_residual_ln_fwd(w.pre32, w.x32[l], P + o[MAGB200_LOFF_LN1_W], P + o[MAGB200_LOFF_LN1_B], d.ln_eps,
@@ -237,8 +239,8 @@ int bert_backward(const magb200_bert_dims& d, const int64_t* off, const float* P
     RUN(linear_wgrad(w.dpre16, H, L.ctx16, H, T, H, H, G + o[MAGB200_LOFF_AO_W], H, 4, us, st));
     RUN(linear_dgrad(w.dpre16, H, P16 + o[MAGB200_LOFF_AO_W], H, T, H, H, EPI_STORE_F16, w.dctx16, nullptr, H, st));
     // BertSelfAttention
-    RUN(sdpa_bwd(L.qkv16, w.dctx16, mask, B, S, d.heads, H / d.heads, d.p_attn, sd, site_attn_prob(l), w.dqkv16, st));
-    RUN(colsum_f16(w.dqkv16, T, 3 * H, us, G + o[MAGB200_LOFF_QKV_B], st));
+    RUN(sdpa_bwd(L.qkv16, w.dctx16, L.ctx16, L.lse, mask, B, S, d.heads, H / d.heads, d.p_attn, sd, site_attn_prob(l), us,
+                 w.dqkv16, G + o[MAGB200_LOFF_QKV_B], st));
     RUN(linear_wgrad(w.dqkv16, 3 * H, w.x16[l], H, T, 3 * H, H, G + o[MAGB200_LOFF_QKV_W], H, 2, us, st));
     RUN(linear_dgrad(w.dqkv16, 3 * H, P16 + o[MAGB200_LOFF_QKV_W], H, T, H, 3 * H, EPI_STORE_F32, w.dy32, w.dy32, H, st));
   }

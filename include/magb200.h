@@ -45,6 +45,11 @@ unsigned long long magb200_launch_count(void);
 /* 0 iff the current device is an sm_100 part */
 int magb200_device_check(void);
 
+/* tuning/debug hook: trace_dev (device, 64 x uint64 per CTA, or NULL) receives clock64 stamps of the GEMM
+ * pipeline; cfg selects the tile configuration (0 = default 128x128x3 stages, 1 = 4 stages, 2 = 6 stages,
+ * 3 = 128x256x3, 4 = 128x256x4). */
+void magb200_gemm_set_debug(void* trace_dev, int cfg);
+
 /* D[M,N] = A[M,K] * B[N,K]^T on tcgen05 tensor cores (TMA-fed, TMEM accumulators).
  * Replaces every nn.Linear / einsum contraction on the reference path (F.linear at
  * modeling.py:27-30; BertSelfAttention/BertSelfOutput/BertIntermediate/BertOutput Linears
@@ -119,11 +124,16 @@ int magb200_colsum_f16(const void* in_f16, int T, int N, float out_scale, float*
 
 /* BertSelfAttention core (transformers 3.0.2, inside bert.py:221-229):
  *   ctx = dropout(softmax(q k^T / 8 + (1 - mask) * -10000)) v  per (batch, head)
- * qkv16 [B*S][3*heads*64] fp16 (q | k | v), mask [B][S] int64 (1 = attend) or NULL, ctx16 [B*S][heads*64] */
+ * qkv16 [B*S][3*heads*64] fp16 (q | k | v), mask [B][S] int64 (1 = attend) or NULL, ctx16 [B*S][heads*64]
+ * lse (optional, [B][heads][S] fp32): forward writes max + log-sum-exp of every score row; with lse and ctx16
+ * present and S <= 64 the warp-MMA kernels run (probabilities never leave registers), otherwise the general
+ * kernels (forward S <= 512, backward S <= 128).  dbias (optional) += out_scale * column sums of dqkv, i.e. the
+ * gradient of the fused query|key|value bias. */
 int magb200_sdpa_fwd(const void* qkv16, const int64_t* mask, int B, int S, int heads, int head_dim, float p,
-                     uint64_t seed, uint32_t site, void* ctx16, void* stream);
-int magb200_sdpa_bwd(const void* qkv16, const void* dctx16, const int64_t* mask, int B, int S, int heads, int head_dim,
-                     float p, uint64_t seed, uint32_t site, void* dqkv16, void* stream);
+                     uint64_t seed, uint32_t site, void* ctx16, float* lse, void* stream);
+int magb200_sdpa_bwd(const void* qkv16, const void* dctx16, const void* ctx16, const float* lse, const int64_t* mask,
+                     int B, int S, int heads, int head_dim, float p, uint64_t seed, uint32_t site, float out_scale,
+                     void* dqkv16, float* dbias, void* stream);
 
 /* BertPooler tanh + dropout + classifier (bert.py:231, 304-307): pre [B][768] = pooler dense output */
 int magb200_cls_fwd(const float* pre, const float* Wc, const float* bc, int B, int num_labels, float p, uint64_t seed,

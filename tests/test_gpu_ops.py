@@ -152,14 +152,15 @@ def test_dropout_residual_ln_fwd_bwd(p):
     assert rel_err(dbias, pre.grad.sum(0)) < 1e-3
 
 
-@pytest.mark.parametrize("S,p", [(50, 0.0), (50, 0.1), (17, 0.0), (128, 0.0)])
-def test_sdpa_fwd_bwd(S, p):
+@pytest.mark.parametrize("S,p,mma", [(50, 0.0, True), (50, 0.1, True), (17, 0.0, True), (64, 0.1, True), (1, 0.0, True),
+                                     (50, 0.1, False), (128, 0.0, False)])
+def test_sdpa_fwd_bwd(S, p, mma):
     g = _g(4)
     B, heads, d = 3, 12, 64
     qkv = (torch.randn(B * S, 3 * heads * d, generator=g) * 0.7).half()
     mask = torch.ones(B, S, dtype=torch.int64)
     mask[1, S // 2:] = 0
-    mask[2, 3:] = 0
+    mask[2, min(3, S - 1):] = 0
     seed, site = 77, 16
     x = qkv.float().view(B, S, 3, heads, d).permute(2, 0, 3, 1, 4).requires_grad_(True)   # [3,B,h,S,d]
     q, k, v = x[0], x[1], x[2]
@@ -173,23 +174,30 @@ def test_sdpa_fwd_bwd(S, p):
     dqkv_ref = x.grad.permute(1, 3, 0, 2, 4).reshape(B * S, 3 * heads * d)
     ctx = torch.empty(B * S, heads * d, device="cuda", dtype=torch.float16)
     qkv_d, mask_d, dctx_d = qkv.cuda(), mask.cuda(), dctx.cuda()
-    L.check(lib().magb200_sdpa_fwd(L.ptr(qkv_d), L.ptr(mask_d), B, S, heads, d, p, seed, site, L.ptr(ctx),
+    # lse + ctx present and S <= 64 -> warp-MMA kernels; lse = NULL -> general kernels
+    lse = torch.zeros(B * heads * S, device="cuda") if mma else None
+    L.check(lib().magb200_sdpa_fwd(L.ptr(qkv_d), L.ptr(mask_d), B, S, heads, d, p, seed, site, L.ptr(ctx), L.ptr(lse),
                                    stream()))
     assert (ctx.float().cpu() - ctx_ref.detach()).abs().max().item() < 4e-3
-    dqkv = torch.empty(B * S, 3 * heads * d, device="cuda", dtype=torch.float16)
-    L.check(lib().magb200_sdpa_bwd(L.ptr(qkv_d), L.ptr(dctx_d), L.ptr(mask_d), B, S, heads, d, p, seed,
-                                   site, L.ptr(dqkv), stream()))
-    assert rel_err(dqkv.float(), dqkv_ref) < 5e-3
+    if mma:
+        lse_ref = torch.logsumexp(s.detach(), dim=-1).reshape(-1)
+        assert (lse.cpu() - lse_ref).abs().max().item() < 2e-3
+    dqkv = torch.zeros(B * S, 3 * heads * d, device="cuda", dtype=torch.float16)
+    dbias = torch.zeros(3 * heads * d, device="cuda")
+    L.check(lib().magb200_sdpa_bwd(L.ptr(qkv_d), L.ptr(dctx_d), L.ptr(ctx) if mma else None, L.ptr(lse), L.ptr(mask_d), B,
+                                   S, heads, d, p, seed, site, 0.5, L.ptr(dqkv), L.ptr(dbias), stream()))
+    assert rel_err(dqkv.float(), dqkv_ref) < 6e-3
+    assert rel_err(dbias, 0.5 * dqkv_ref.sum(0)) < 1e-2
 
 
 def test_sdpa_without_mask_and_range_errors():
     B, S, heads, d = 1, 8, 12, 64
     qkv = torch.randn(B * S, 3 * heads * d).half().cuda()
     ctx = torch.empty(B * S, heads * d, device="cuda", dtype=torch.float16)
-    L.check(lib().magb200_sdpa_fwd(L.ptr(qkv), None, B, S, heads, d, 0.0, 0, 0, L.ptr(ctx), stream()))
+    L.check(lib().magb200_sdpa_fwd(L.ptr(qkv), None, B, S, heads, d, 0.0, 0, 0, L.ptr(ctx), None, stream()))
     assert torch.isfinite(ctx).all()
-    assert lib().magb200_sdpa_fwd(L.ptr(qkv), None, B, 513, heads, d, 0.0, 0, 0, L.ptr(ctx), stream()) != 0
-    assert lib().magb200_sdpa_fwd(L.ptr(qkv), None, B, S, heads, 32, 0.0, 0, 0, L.ptr(ctx), stream()) != 0
+    assert lib().magb200_sdpa_fwd(L.ptr(qkv), None, B, 513, heads, d, 0.0, 0, 0, L.ptr(ctx), None, stream()) != 0
+    assert lib().magb200_sdpa_fwd(L.ptr(qkv), None, B, S, heads, 32, 0.0, 0, 0, L.ptr(ctx), None, stream()) != 0
 
 
 @pytest.mark.parametrize("name", ["mag_mosi", "mag_mosi_zero_rows_beta1e-3", "mag_mosei"])
