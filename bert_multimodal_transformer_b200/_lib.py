@@ -29,6 +29,23 @@ OFF_PER_LAYER = 12
 PEEK_EMB, PEEK_MAG, PEEK_LAYER_OUT, PEEK_POOLED, PEEK_GATES = range(5)
 
 
+# XLNet offsets (include/magb200.h: MAGB200_XOFF_* / MAGB200_XLOFF_*)
+(XOFF_WORD, XOFF_MAG_WHV, XOFF_MAG_WHA, XOFF_MAG_WV, XOFF_MAG_WA, XOFF_MAG_BIAS4, XOFF_MAG_LN_W, XOFF_MAG_LN_B,
+ XOFF_SUM_W, XOFF_SUM_B, XOFF_CLS_W, XOFF_CLS_B, XOFF_MAG_PACKED16, XOFF_TOTAL) = range(14)
+XOFF_LAYER0 = 16
+(XLOFF_Q, XLOFF_K, XLOFF_V, XLOFF_O, XLOFF_R, XLOFF_RR_BIAS, XLOFF_RS_BIAS, XLOFF_RW_BIAS, XLOFF_SEG, XLOFF_LN1_W,
+ XLOFF_LN1_B, XLOFF_F1_W, XLOFF_F1_B, XLOFF_F2_W, XLOFF_F2_B, XLOFF_LN2_W, XLOFF_LN2_B, XLOFF_QKV_PACKED16) = range(18)
+XOFF_PER_LAYER = 18
+
+
+class XlnetDims(Structure):
+    """struct magb200_xlnet_dims (include/magb200.h)."""
+    _fields_ = [(n, c_int32) for n in ("batch", "seq", "hidden", "heads", "inter", "layers", "vocab", "visual_dim",
+                                       "acoustic_dim", "num_labels", "ka", "injection_index")] + \
+               [(n, c_float) for n in ("ln_eps", "mag_ln_eps", "beta_shift", "p_drop", "p_mag", "p_summary",
+                                       "grad_scale")] + [("seed", c_uint64), ("seed_dev", c_void_p)]
+
+
 class BertDims(Structure):
     """struct magb200_bert_dims (include/magb200.h)."""
     _fields_ = [(n, c_int32) for n in ("batch", "seq", "hidden", "heads", "inter", "layers", "vocab", "max_pos",
@@ -82,6 +99,18 @@ SIGNATURES = {
     "magb200_bert_backward": (c_int, [POINTER(BertDims), POINTER(c_int64)] + [c_void_p] * 6 + [c_size_t, c_void_p,
                                                                                                c_void_p, c_void_p]),
     "magb200_bert_peek": (c_int, [POINTER(BertDims), c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "magb200_xlnet_workspace_bytes": (c_size_t, [POINTER(XlnetDims)]),
+    "magb200_xlnet_refresh_operands": (c_int, [POINTER(XlnetDims), POINTER(c_int64), c_void_p, c_void_p, c_void_p]),
+    "magb200_xlnet_forward": (c_int, [POINTER(XlnetDims), POINTER(c_int64)] + [c_void_p] * 8 + [c_size_t, c_void_p,
+                                                                                                c_void_p]),
+    "magb200_xlnet_backward": (c_int, [POINTER(XlnetDims), POINTER(c_int64)] + [c_void_p] * 6 + [c_size_t, c_void_p,
+                                                                                                 c_void_p, c_void_p]),
+    "magb200_xlnet_peek": (c_int, [POINTER(XlnetDims), c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "magb200_xlnet_rel_attn_fwd": (c_int, [c_void_p, c_void_p, c_int] + [c_void_p] * 6 + [c_int] * 4
+                                   + [c_float, c_uint64, c_uint32, c_void_p, c_void_p]),
+    "magb200_xlnet_rel_attn_bwd": (c_int, [c_void_p, c_void_p, c_int] + [c_void_p] * 7 + [c_int] * 4
+                                   + [c_float, c_uint64, c_uint32, c_float] + [c_void_p] * 7),
+    "magb200_xlnet_pos_emb": (c_int, [c_int, c_int, c_float, c_uint64, c_uint32, c_void_p, c_void_p]),
 }
 
 

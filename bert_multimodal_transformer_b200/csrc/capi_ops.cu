@@ -170,3 +170,70 @@ int magb200_bert_peek(const magb200_bert_dims* dims, void* workspace, int what, 
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ XLNet
+extern "C" {
+
+size_t magb200_xlnet_workspace_bytes(const magb200_xlnet_dims* dims) { return xlnet_workspace_bytes(*dims); }
+
+int magb200_xlnet_refresh_operands(const magb200_xlnet_dims* dims, const int64_t* off, const float* params,
+                                   void* params16, void* stream) {
+  return xlnet_refresh_operands(*dims, off, params, reinterpret_cast<__half*>(params16), ST);
+}
+
+int magb200_xlnet_forward(const magb200_xlnet_dims* dims, const int64_t* off, const float* params, const void* params16,
+                          const int64_t* input_ids, const int64_t* token_type_ids, const int64_t* attention_mask,
+                          const float* visual, const float* acoustic, void* workspace, size_t workspace_bytes,
+                          float* logits, void* stream) {
+  return xlnet_forward(*dims, off, params, reinterpret_cast<const __half*>(params16), input_ids, token_type_ids,
+                       attention_mask, visual, acoustic, workspace, workspace_bytes, logits, ST);
+}
+
+int magb200_xlnet_backward(const magb200_xlnet_dims* dims, const int64_t* off, const float* params, const void* params16,
+                           const int64_t* input_ids, const int64_t* token_type_ids, const int64_t* attention_mask,
+                           void* workspace, size_t workspace_bytes, const float* dlogits_scaled, float* grads,
+                           void* stream) {
+  return xlnet_backward(*dims, off, params, reinterpret_cast<const __half*>(params16), input_ids, token_type_ids,
+                        attention_mask, workspace, workspace_bytes, dlogits_scaled, grads, ST);
+}
+
+int magb200_xlnet_peek(const magb200_xlnet_dims* dims, void* workspace, int what, int layer, void* out,
+                       size_t out_bytes, void* stream) {
+  return xlnet_peek(*dims, workspace, what, layer, out, out_bytes, ST);
+}
+
+static RelAttnArgs make_rel(const void* qkv16, const void* kr16, int Bp, const float* r_w_bias, const float* r_r_bias,
+                            const float* r_s_bias, const float* seg_embed, const int64_t* mask, const int64_t* tt, int B,
+                            int S, int heads, int head_dim, float p, uint64_t seed, uint32_t site) {
+  RelAttnArgs a;
+  a.qkv = reinterpret_cast<const __half*>(qkv16); a.kr16 = reinterpret_cast<const __half*>(kr16); a.Bp = Bp;
+  a.r_w_bias = r_w_bias; a.r_r_bias = r_r_bias; a.r_s_bias = r_s_bias; a.seg_embed = seg_embed; a.mask = mask; a.tt = tt;
+  a.B = B; a.S = S; a.heads = heads; a.head_dim = head_dim; a.p = p; a.seed = Seed{seed, nullptr}; a.site = site;
+  return a;
+}
+
+int magb200_xlnet_rel_attn_fwd(const void* qkv16, const void* kr16, int Bp, const float* r_w_bias, const float* r_r_bias,
+                               const float* r_s_bias, const float* seg_embed, const int64_t* attention_mask,
+                               const int64_t* token_type_ids, int B, int S, int heads, int head_dim, float p, uint64_t seed,
+                               uint32_t site, void* ctx16, void* stream) {
+  return xl_rel_attn_fwd(make_rel(qkv16, kr16, Bp, r_w_bias, r_r_bias, r_s_bias, seg_embed, attention_mask, token_type_ids,
+                                  B, S, heads, head_dim, p, seed, site),
+                         reinterpret_cast<__half*>(ctx16), ST);
+}
+
+int magb200_xlnet_rel_attn_bwd(const void* qkv16, const void* kr16, int Bp, const float* r_w_bias, const float* r_r_bias,
+                               const float* r_s_bias, const float* seg_embed, const int64_t* attention_mask,
+                               const int64_t* token_type_ids, const void* dctx16, int B, int S, int heads, int head_dim,
+                               float p, uint64_t seed, uint32_t site, float out_scale, void* dqkv16, float* dkr32,
+                               float* d_r_w_bias, float* d_r_r_bias, float* d_r_s_bias, float* d_seg_embed, void* stream) {
+  return xl_rel_attn_bwd(make_rel(qkv16, kr16, Bp, r_w_bias, r_r_bias, r_s_bias, seg_embed, attention_mask, token_type_ids,
+                                  B, S, heads, head_dim, p, seed, site),
+                         reinterpret_cast<const __half*>(dctx16), out_scale, reinterpret_cast<__half*>(dqkv16), dkr32,
+                         d_r_w_bias, d_r_r_bias, d_r_s_bias, d_seg_embed, ST);
+}
+
+int magb200_xlnet_pos_emb(int S, int Bp, float p, uint64_t seed, uint32_t site, void* pos16, void* stream) {
+  return xl_pos_emb(S, Bp, p, Seed{seed, nullptr}, site, reinterpret_cast<__half*>(pos16), ST);
+}
+
+}  // extern "C"

@@ -156,6 +156,15 @@ int gemm_launch(const GemmProblem& p, cudaStream_t st) {
   const uint32_t bf = p.b_dtype == DT_F32 ? 2u : (p.b_dtype == DT_BF16 ? 1u : 0u);
   g.idesc = make_idesc(af, bf, p.a_mn, p.b_mn, BM, BN);
   g.trace = g_trace;
+  g.drop_thresh = 0; g.drop_scale = 1.f; g.drop_site = p.drop_site; g.drop_seed = p.drop_seed.value;
+  g.drop_seed_ptr = reinterpret_cast<const unsigned long long*>(p.drop_seed.ptr);
+  if (p.drop_p > 0.f) {
+    MAGB_REQUIRE(p.epi == EPI_GELU_F16 || p.epi == EPI_DGELU_F16, "gemm: fused dropout is only available in the GELU epilogues");
+    MAGB_REQUIRE(p.N % 4 == 0, "gemm: fused dropout needs N % 4 == 0");
+    const double t = (double)p.drop_p * 4294967296.0;
+    g.drop_thresh = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
+    g.drop_scale = 1.0f / (1.0f - p.drop_p);
+  }
 
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, splits);
   if (EB == 2) {

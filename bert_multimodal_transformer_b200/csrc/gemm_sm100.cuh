@@ -46,6 +46,13 @@ struct GemmArgs {
   float alpha;
   uint32_t idesc;
   unsigned long long* trace;   // debug: per-CTA clock64 stamps (64 slots per CTA) or null
+  // optional dropout fused into the GELU / GELU' epilogues (XLNetFeedForward drops the activation):
+  // keep-mask = philox(seed, site, (m * N + n) / 4), scale 1/(1-p); thresh == 0 disables it
+  uint32_t drop_thresh;
+  float drop_scale;
+  uint32_t drop_site;
+  unsigned long long drop_seed;
+  const unsigned long long* drop_seed_ptr;
 };
 
 template <int EB>
@@ -150,6 +157,19 @@ __device__ __forceinline__ void row_write_16(uint8_t* row, int c, const float (&
   }
 }
 
+// v[32] = columns [n, n+32) of row m: zero the dropped elements, scale the kept ones
+__device__ __forceinline__ void epi_dropout(const GemmArgs& g, int m, int n, float (&v)[32]) {
+  const unsigned long long seed = g.drop_seed_ptr ? *g.drop_seed_ptr : g.drop_seed;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint4 u = philox4x32(seed, g.drop_site, ((unsigned long long)m * g.N + n + 4 * j) >> 2);
+    v[4 * j] = u.x >= g.drop_thresh ? v[4 * j] * g.drop_scale : 0.f;
+    v[4 * j + 1] = u.y >= g.drop_thresh ? v[4 * j + 1] * g.drop_scale : 0.f;
+    v[4 * j + 2] = u.z >= g.drop_thresh ? v[4 * j + 2] * g.drop_scale : 0.f;
+    v[4 * j + 3] = u.w >= g.drop_thresh ? v[4 * j + 3] * g.drop_scale : 0.f;
+  }
+}
+
 // One epilogue warp: rows [m_base, m_base+32) x columns [n0, n0+BN) of the output.
 template <int BN>
 __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& g, uint32_t tmem_warp, int m_base, int n0,
@@ -220,6 +240,7 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& g, uint32_t t
           if (!(npass == 2 && pass == 0)) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+            if (g.drop_thresh != 0) epi_dropout(g, m_base + lane, n0 + c * 32, v);
           }
           row_write_16<false>(myrow, c, v);
           break;
@@ -236,6 +257,7 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& g, uint32_t t
               v[8 * j + 2 * t + 1] *= gelu_erf_grad(f.y);
             }
           }
+          if (g.drop_thresh != 0) epi_dropout(g, m_base + lane, n0 + c * 32, v);
           row_write_16<false>(myrow, c, v);
         } break;
         default: break;

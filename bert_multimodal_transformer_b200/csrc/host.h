@@ -31,6 +31,10 @@ struct GemmProblem {
   const void* aux = nullptr;
   int ldo = 0;
   float alpha = 1.0f;
+  // dropout fused into the GELU / GELU' epilogues (p = 0: off); element index = m * N + n
+  float drop_p = 0.f;
+  Seed drop_seed;
+  uint32_t drop_site = 0;
 };
 
 int gemm_launch(const GemmProblem& p, cudaStream_t stream);
@@ -98,6 +102,31 @@ int adamw_step(float* p, float* g, float* m, float* v, __half* p16, const uint8_
                float b1, float b2, float eps, float wd, int step, float gscale, int zero_grad, const float* hyper_dev,
                cudaStream_t st);
 
+
+// ---------------------------------------------------------------- xlnet_ops.cu
+struct RelAttnArgs {
+  const __half* qkv = nullptr;      // [B*S][3*heads*64]  (q | k | v head projections, no bias)
+  const __half* kr16 = nullptr;     // [Bp][2S][heads*64] projected relative positions (Bp = 1 or B)
+  int Bp = 1;
+  const float* r_w_bias = nullptr; const float* r_r_bias = nullptr; const float* r_s_bias = nullptr;   // [heads][64]
+  const float* seg_embed = nullptr; // [2][heads][64]
+  const int64_t* mask = nullptr;    // [B][S] attention_mask (1 = token, 0 = pad) or null
+  const int64_t* tt = nullptr;      // [B][S] segment ids or null
+  int B = 0, S = 0, heads = 12, head_dim = 64;
+  float p = 0.f; Seed seed; uint32_t site = 0;
+};
+int xl_gather_fwd(const int64_t* ids, const float* word, int T, int vocab, float p, Seed seed, uint32_t site, float* x32,
+                  __half* x16, cudaStream_t st);
+int xl_gather_bwd(const float* dx, const int64_t* ids, int T, int vocab, float p, Seed seed, uint32_t site, float oscale,
+                  float* dword, cudaStream_t st);
+int xl_pos_emb(int S, int Bp, float p, Seed seed, uint32_t site, __half* pos16, cudaStream_t st);
+int xl_last_token_fwd(const float* x32, int B, int S, float p, Seed seed, uint32_t site, __half* out16, cudaStream_t st);
+int xl_last_token_bwd(const float* dlast, int B, int S, float p, Seed seed, uint32_t site, float* dx32, cudaStream_t st);
+int xl_pack_qkv(const float* q, const float* k, const float* v, __half* out, cudaStream_t st);
+int xl_rel_attn_fwd(const RelAttnArgs& a, __half* ctx, cudaStream_t st);
+int xl_rel_attn_bwd(const RelAttnArgs& a, const __half* dctx, float oscale, __half* dqkv, float* dkr32, float* d_rw,
+                    float* d_rr, float* d_rs, float* d_seg, cudaStream_t st);
+
 }  // namespace magb200
 
 // ---------------------------------------------------------------- model_bert.cu
@@ -114,5 +143,21 @@ int bert_backward(const magb200_bert_dims& d, const int64_t* off, const float* P
                   float* G, cudaStream_t st);
 int bert_peek(const magb200_bert_dims& d, void* workspace, int what, int layer, void* out, size_t out_bytes,
               cudaStream_t st);
+}  // namespace magb200
+
+// ---------------------------------------------------------------- model_xlnet.cu
+struct magb200_xlnet_dims;
+namespace magb200 {
+size_t xlnet_workspace_bytes(const magb200_xlnet_dims& d);
+int xlnet_refresh_operands(const magb200_xlnet_dims& d, const int64_t* off, const float* params, __half* params16,
+                           cudaStream_t st);
+int xlnet_forward(const magb200_xlnet_dims& d, const int64_t* off, const float* P, const __half* P16, const int64_t* ids,
+                  const int64_t* tt, const int64_t* mask, const float* visual, const float* acoustic, void* workspace,
+                  size_t ws_bytes, float* logits, cudaStream_t st);
+int xlnet_backward(const magb200_xlnet_dims& d, const int64_t* off, const float* P, const __half* P16, const int64_t* ids,
+                   const int64_t* tt, const int64_t* mask, void* workspace, size_t ws_bytes, const float* dlogits_scaled,
+                   float* G, cudaStream_t st);
+int xlnet_peek(const magb200_xlnet_dims& d, void* workspace, int what, int layer, void* out, size_t out_bytes,
+               cudaStream_t st);
 }  // namespace magb200
 

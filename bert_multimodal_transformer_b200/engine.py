@@ -98,6 +98,19 @@ class BertEngine:
                                                   L.current_stream()))
         self.operands_dirty = False
 
+    def workspace_bytes(self, dims):
+        return L.load().magb200_bert_workspace_bytes(byref(dims))
+
+    def after_optimizer_step(self):
+        """fp32 masters changed in place and the fused AdamW already rewrote the fp16 mirror: only the packed
+        MAG gate matrix has to be re-derived."""
+        lib, o, f = L.load(), self.offsets, self.flat
+        L.check(lib.magb200_mag_pack_weights(
+            c_void_p(f.data_ptr() + 4 * o[L.OFF_MAG_WHV]), c_void_p(f.data_ptr() + 4 * o[L.OFF_MAG_WHA]),
+            c_void_p(f.data_ptr() + 4 * o[L.OFF_MAG_WV]), c_void_p(f.data_ptr() + 4 * o[L.OFF_MAG_WA]),
+            self.visual_dim, self.acoustic_dim, self.ka, c_void_p(self.flat16.data_ptr() + 2 * o[L.OFF_MAG_PACKED16]),
+            L.current_stream()))
+
     def workspace(self, dims, keep: bool) -> torch.Tensor:
         lib = L.load()
         nbytes = lib.magb200_bert_workspace_bytes(byref(dims))
@@ -145,3 +158,119 @@ def prep_inputs(device, input_ids, visual, acoustic, attention_mask, token_type_
     mask = None if attention_mask is None else attention_mask.to(device=device, dtype=torch.int64).contiguous()
     tt = None if token_type_ids is None else token_type_ids.to(device=device, dtype=torch.int64).contiguous()
     return ids, vis, aco, mask, tt
+
+
+class XlnetEngine:
+    """Host-side driver of magb200_xlnet_forward / _backward (same role as BertEngine)."""
+
+    def __init__(self, *, hidden, heads, inter, layers, vocab, visual_dim, acoustic_dim, num_labels, ln_eps, beta_shift,
+                 p_drop, p_mag, p_summary, injection_index=1, grad_scale=1024.0):
+        if hidden != 768 or heads != 12:
+            raise NotImplementedError("libmagb200 kernels are specialised for d_model=768, 12 heads (xlnet-base)")
+        from .flat import xlnet_param_order
+        self.hidden, self.heads, self.inter, self.layers, self.vocab = hidden, heads, inter, layers, vocab
+        self.visual_dim, self.acoustic_dim, self.num_labels = visual_dim, acoustic_dim, num_labels
+        self.ln_eps, self.beta_shift = ln_eps, beta_shift
+        self.p_drop, self.p_mag, self.p_summary = p_drop, p_mag, p_summary
+        self.injection_index = injection_index
+        self.grad_scale = float(grad_scale)
+        self.ka = hidden + 128
+        self.order = xlnet_param_order(layers)
+        self.layout = None
+        self.flat = None
+        self.flat16 = None
+        self.offsets = None
+        self.operands_dirty = True
+        self._eval_ws = {}
+        self._expected_ptrs = None
+
+    def bind(self, named_params):
+        from .flat import xlnet_fp16_numel, xlnet_offsets_table
+        missing = [n for n in self.order if n not in named_params]
+        if missing:
+            raise KeyError(f"parameters missing from the model: {missing[:4]}...")
+        dev = named_params[self.order[0]].device
+        _require_cuda(named_params[self.order[0]], "model parameters")
+        if self.layout is None:
+            self.layout = FlatLayout([(n, tuple(named_params[n].shape)) for n in self.order])
+            self.offsets = xlnet_offsets_table(self.layout, self.layers, self.hidden, self.ka)
+        flat = torch.zeros(self.layout.total, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for n in self.order:
+                p = named_params[n]
+                v = self.layout.view(flat, n)
+                v.copy_(p.detach().to(device=dev, dtype=torch.float32))
+                p.data = v
+        self.flat = flat
+        self.flat16 = torch.zeros(xlnet_fp16_numel(self.layout, self.layers, self.hidden, self.ka), dtype=torch.float16,
+                                  device=dev)
+        self._expected_ptrs = [(named_params[n], self.layout.view(flat, n).data_ptr()) for n in self.order]
+        self.operands_dirty = True
+        self._eval_ws.clear()
+
+    def is_bound(self):
+        if self.flat is None:
+            return False
+        return all(p.data_ptr() == ptr for p, ptr in self._expected_ptrs)
+
+    def dims(self, batch, seq, training, seed=0) -> L.XlnetDims:
+        d = L.XlnetDims()
+        d.batch, d.seq, d.hidden, d.heads, d.inter, d.layers, d.vocab = batch, seq, self.hidden, self.heads, self.inter, \
+            self.layers, self.vocab
+        d.visual_dim, d.acoustic_dim, d.num_labels, d.ka = self.visual_dim, self.acoustic_dim, self.num_labels, self.ka
+        d.injection_index = self.injection_index
+        d.ln_eps, d.mag_ln_eps, d.beta_shift = self.ln_eps, 1e-5, self.beta_shift
+        if training:
+            d.p_drop, d.p_mag, d.p_summary = self.p_drop, self.p_mag, self.p_summary
+        else:
+            d.p_drop = d.p_mag = d.p_summary = 0.0
+        d.grad_scale = self.grad_scale
+        d.seed = seed
+        return d
+
+    def refresh_operands(self, dims=None):
+        lib = L.load()
+        d = dims or self.dims(1, 1, False)
+        L.check(lib.magb200_xlnet_refresh_operands(byref(d), self.offsets, L.ptr(self.flat), L.ptr(self.flat16),
+                                                   L.current_stream()))
+        self.operands_dirty = False
+
+    def workspace_bytes(self, dims):
+        return L.load().magb200_xlnet_workspace_bytes(byref(dims))
+
+    def workspace(self, dims, keep):
+        nbytes = self.workspace_bytes(dims)
+        if keep:
+            return torch.empty(nbytes, dtype=torch.uint8, device=self.flat.device)
+        key = (dims.batch, dims.seq, dims.p_drop > 0)
+        ws = self._eval_ws.get(key)
+        if ws is None or ws.numel() < nbytes:
+            self._eval_ws.clear()
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=self.flat.device)
+            self._eval_ws[key] = ws
+        return ws
+
+    def forward(self, dims, ws, input_ids, token_type_ids, attention_mask, visual, acoustic, logits):
+        L.check(L.load().magb200_xlnet_forward(byref(dims), self.offsets, L.ptr(self.flat), L.ptr(self.flat16),
+                                               L.ptr(input_ids), L.ptr(token_type_ids), L.ptr(attention_mask),
+                                               L.ptr(visual), L.ptr(acoustic), L.ptr(ws), ws.numel(), L.ptr(logits),
+                                               L.current_stream()))
+
+    def backward(self, dims, ws, input_ids, token_type_ids, attention_mask, dlogits_scaled, grads):
+        L.check(L.load().magb200_xlnet_backward(byref(dims), self.offsets, L.ptr(self.flat), L.ptr(self.flat16),
+                                                L.ptr(input_ids), L.ptr(token_type_ids), L.ptr(attention_mask),
+                                                L.ptr(ws), ws.numel(), L.ptr(dlogits_scaled), L.ptr(grads),
+                                                L.current_stream()))
+
+    def peek(self, dims, ws, what, layer=0):
+        shape = {L.PEEK_MAG: (dims.batch, dims.seq, self.hidden), L.PEEK_LAYER_OUT: (dims.batch, dims.seq, self.hidden),
+                 L.PEEK_POOLED: (dims.batch, self.hidden)}[what]
+        out = torch.empty(shape, dtype=torch.float32, device=self.flat.device)
+        L.check(L.load().magb200_xlnet_peek(byref(dims), L.ptr(ws), what, layer, L.ptr(out), out.numel() * 4,
+                                            L.current_stream()))
+        return out
+
+    def after_optimizer_step(self):
+        """fp32 masters changed in place (fused AdamW already rewrote the fp16 mirror): re-pack the derived
+        operands (MAG gate matrix, per-layer q|k|v).  The cast inside refresh is redundant but cheap."""
+        self.refresh_operands()

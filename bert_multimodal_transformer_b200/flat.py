@@ -131,3 +131,67 @@ def bert_offsets_table(layout: FlatLayout, num_layers: int, hidden: int, ka: int
 
 def packed16_numel(hidden: int, ka: int) -> int:
     return 4 * hidden * ka
+
+
+# ------------------------------------------------------------------------------------------------ XLNet
+def xlnet_param_order(num_layers: int) -> List[str]:
+    """State-dict keys of MAG_XLNetForSequenceClassification in flat order.
+    `transformer.mask_emb` is not part of the flat buffer: the content-stream path never reads it
+    (xlnet.py:306-313) and it receives no gradient."""
+    names = ["transformer.word_embedding.weight"]
+    for i in range(num_layers):
+        p = f"transformer.layer.{i}."
+        names += [p + "rel_attn.q", p + "rel_attn.k", p + "rel_attn.v", p + "rel_attn.o", p + "rel_attn.r",
+                  p + "rel_attn.r_r_bias", p + "rel_attn.r_s_bias", p + "rel_attn.r_w_bias", p + "rel_attn.seg_embed",
+                  p + "rel_attn.layer_norm.weight", p + "rel_attn.layer_norm.bias",
+                  p + "ff.layer_1.weight", p + "ff.layer_1.bias", p + "ff.layer_2.weight", p + "ff.layer_2.bias",
+                  p + "ff.layer_norm.weight", p + "ff.layer_norm.bias"]
+    names += ["transformer.MAG.W_hv.weight", "transformer.MAG.W_ha.weight", "transformer.MAG.W_v.weight",
+              "transformer.MAG.W_a.weight", "transformer.MAG.W_hv.bias", "transformer.MAG.W_ha.bias",
+              "transformer.MAG.W_v.bias", "transformer.MAG.W_a.bias", "transformer.MAG.LayerNorm.weight",
+              "transformer.MAG.LayerNorm.bias", "sequence_summary.summary.weight", "sequence_summary.summary.bias",
+              "logits_proj.weight", "logits_proj.bias"]
+    return names
+
+
+def xlnet_offsets_table(layout: FlatLayout, num_layers: int, hidden: int, ka: int):
+    """int64[] for magb200_xlnet_* (MAGB200_XOFF_* / MAGB200_XLOFF_*).  The fp16 buffer holds, after the
+    mirrored region: the packed MAG gate matrix, then one packed [768][2304] q|k|v operand per layer."""
+    n = L.XOFF_LAYER0 + L.XOFF_PER_LAYER * num_layers
+    t = (ctypes.c_int64 * n)()
+    o = layout.offset
+    t[L.XOFF_WORD] = o("transformer.word_embedding.weight")
+    t[L.XOFF_MAG_WHV] = o("transformer.MAG.W_hv.weight")
+    t[L.XOFF_MAG_WHA] = o("transformer.MAG.W_ha.weight")
+    t[L.XOFF_MAG_WV] = o("transformer.MAG.W_v.weight")
+    t[L.XOFF_MAG_WA] = o("transformer.MAG.W_a.weight")
+    t[L.XOFF_MAG_BIAS4] = o("transformer.MAG.W_hv.bias")
+    for k, nm in enumerate(("W_hv", "W_ha", "W_v", "W_a")):
+        assert o(f"transformer.MAG.{nm}.bias") == t[L.XOFF_MAG_BIAS4] + k * hidden
+    t[L.XOFF_MAG_LN_W] = o("transformer.MAG.LayerNorm.weight")
+    t[L.XOFF_MAG_LN_B] = o("transformer.MAG.LayerNorm.bias")
+    t[L.XOFF_SUM_W] = o("sequence_summary.summary.weight")
+    t[L.XOFF_SUM_B] = o("sequence_summary.summary.bias")
+    t[L.XOFF_CLS_W] = o("logits_proj.weight")
+    t[L.XOFF_CLS_B] = o("logits_proj.bias")
+    t[L.XOFF_MAG_PACKED16] = layout.total
+    t[L.XOFF_TOTAL] = layout.total
+    extra = layout.total + packed16_numel(hidden, ka)
+    for i in range(num_layers):
+        p = f"transformer.layer.{i}."
+        b = L.XOFF_LAYER0 + L.XOFF_PER_LAYER * i
+        for slot, nm in ((L.XLOFF_Q, "rel_attn.q"), (L.XLOFF_K, "rel_attn.k"), (L.XLOFF_V, "rel_attn.v"),
+                         (L.XLOFF_O, "rel_attn.o"), (L.XLOFF_R, "rel_attn.r"), (L.XLOFF_RR_BIAS, "rel_attn.r_r_bias"),
+                         (L.XLOFF_RS_BIAS, "rel_attn.r_s_bias"), (L.XLOFF_RW_BIAS, "rel_attn.r_w_bias"),
+                         (L.XLOFF_SEG, "rel_attn.seg_embed"), (L.XLOFF_LN1_W, "rel_attn.layer_norm.weight"),
+                         (L.XLOFF_LN1_B, "rel_attn.layer_norm.bias"), (L.XLOFF_F1_W, "ff.layer_1.weight"),
+                         (L.XLOFF_F1_B, "ff.layer_1.bias"), (L.XLOFF_F2_W, "ff.layer_2.weight"),
+                         (L.XLOFF_F2_B, "ff.layer_2.bias"), (L.XLOFF_LN2_W, "ff.layer_norm.weight"),
+                         (L.XLOFF_LN2_B, "ff.layer_norm.bias")):
+            t[b + slot] = o(p + nm)
+        t[b + L.XLOFF_QKV_PACKED16] = extra + i * hidden * 3 * hidden
+    return t
+
+
+def xlnet_fp16_numel(layout: FlatLayout, num_layers: int, hidden: int, ka: int) -> int:
+    return layout.total + packed16_numel(hidden, ka) + num_layers * hidden * 3 * hidden

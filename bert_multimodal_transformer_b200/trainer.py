@@ -37,17 +37,19 @@ def linear_schedule(step: int, warmup: int, total: int) -> float:
 class MagBertTrainer:
     def __init__(self, model, batch_size: int, seq_len: int, lr: float = 1e-5, weight_decay: float = 0.01,
                  betas=(0.9, 0.999), eps: float = 1e-6, warmup_steps: int = 0, total_steps: int = 0,
-                 use_cuda_graph: bool = True, process_group=None, seed: int = 0):
+                 use_cuda_graph: bool = True, process_group=None, seed: int = 0, world_size: Optional[int] = None):
         model._ensure_bound()
         self.model = model
-        self.eng: BertEngine = model._engine
+        self.eng = model._engine      # BertEngine or XlnetEngine
         eng = self.eng
         self.B, self.S = batch_size, seq_len
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
         self.warmup_steps, self.total_steps = warmup_steps, total_steps
         self.pg = process_group
         self.world = 1
-        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        if world_size is not None:
+            self.world = int(world_size)          # explicit override (1 = no gradient all-reduce)
+        elif process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
         dev = eng.flat.device
         self.dev = dev
@@ -85,7 +87,7 @@ class MagBertTrainer:
         self.train_dims.seed_dev = self.dev_seed.data_ptr()
         self.eval_dims = eng.dims(B, S, False, 0)
         lib = L.load()
-        self.ws = torch.empty(lib.magb200_bert_workspace_bytes(byref(self.train_dims)), dtype=torch.uint8, device=dev)
+        self.ws = torch.empty(eng.workspace_bytes(self.train_dims), dtype=torch.uint8, device=dev)
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.slots[0].values()) + 8 + 8
         self.d2h_bytes = 4
         self.use_graph = use_cuda_graph
@@ -124,12 +126,7 @@ class MagBertTrainer:
                                        L.ptr(eng.flat16), L.ptr(self.decay), eng.layout.total, self.lr, self.betas[0],
                                        self.betas[1], self.eps, self.wd, 1, grad_unscale(self.world), 1, L.ptr(self.dev_hyper),
                                        st))
-        o = eng.offsets
-        f = eng.flat
-        L.check(lib.magb200_mag_pack_weights(
-            c_void_p(f.data_ptr() + 4 * o[L.OFF_MAG_WHV]), c_void_p(f.data_ptr() + 4 * o[L.OFF_MAG_WHA]),
-            c_void_p(f.data_ptr() + 4 * o[L.OFF_MAG_WV]), c_void_p(f.data_ptr() + 4 * o[L.OFF_MAG_WA]),
-            eng.visual_dim, eng.acoustic_dim, eng.ka, c_void_p(eng.flat16.data_ptr() + 2 * o[L.OFF_MAG_PACKED16]), st))
+        eng.after_optimizer_step()
         if transfers:
             self.host_loss[slot].copy_(self.loss, non_blocking=True)
 

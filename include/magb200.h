@@ -208,6 +208,70 @@ int magb200_bert_backward(const magb200_bert_dims* dims, const int64_t* off, con
 int magb200_bert_peek(const magb200_bert_dims* dims, void* workspace, int what, int layer, void* out, size_t out_bytes,
                       void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * MAG-XLNet: MAG_XLNetForSequenceClassification.forward (xlnet.py:443-527) through
+ * MAG_XLNetModel.forward (xlnet.py:148-429), content stream only (target_mapping / perm_mask / mems
+ * None -- the path multimodal_driver.py exercises), and its backward.  Tokens are batch-major
+ * (t = b*S + s); the reference's seq-first transposes (xlnet.py:206-239) are layout only.
+ * Flat parameter buffer as for BERT; projection tensors q,k,v,r are [d_model][heads*64] ("in x out"),
+ * o is [d_model][heads*64] read as [out][in].  params16 = fp16 mirror + packed MAG gate matrix
+ * (MAGB200_XOFF_MAG_PACKED16) + per layer the packed [768][2304] q|k|v operand (MAGB200_XLOFF_QKV_PACKED16). */
+enum {
+  MAGB200_XOFF_WORD = 0, MAGB200_XOFF_MAG_WHV, MAGB200_XOFF_MAG_WHA, MAGB200_XOFF_MAG_WV, MAGB200_XOFF_MAG_WA,
+  MAGB200_XOFF_MAG_BIAS4, MAGB200_XOFF_MAG_LN_W, MAGB200_XOFF_MAG_LN_B, MAGB200_XOFF_SUM_W, MAGB200_XOFF_SUM_B,
+  MAGB200_XOFF_CLS_W, MAGB200_XOFF_CLS_B, MAGB200_XOFF_MAG_PACKED16, MAGB200_XOFF_TOTAL,
+  MAGB200_XOFF_LAYER0 = 16
+};
+enum {
+  MAGB200_XLOFF_Q = 0, MAGB200_XLOFF_K, MAGB200_XLOFF_V, MAGB200_XLOFF_O, MAGB200_XLOFF_R, MAGB200_XLOFF_RR_BIAS,
+  MAGB200_XLOFF_RS_BIAS, MAGB200_XLOFF_RW_BIAS, MAGB200_XLOFF_SEG, MAGB200_XLOFF_LN1_W, MAGB200_XLOFF_LN1_B,
+  MAGB200_XLOFF_F1_W, MAGB200_XLOFF_F1_B, MAGB200_XLOFF_F2_W, MAGB200_XLOFF_F2_B, MAGB200_XLOFF_LN2_W,
+  MAGB200_XLOFF_LN2_B, MAGB200_XLOFF_QKV_PACKED16, MAGB200_XOFF_PER_LAYER = 18
+};
+
+typedef struct magb200_xlnet_dims {
+  int32_t batch, seq, hidden, heads, inter, layers, vocab, visual_dim, acoustic_dim, num_labels, ka, injection_index;
+  float ln_eps, mag_ln_eps, beta_shift;
+  float p_drop, p_mag, p_summary;                      /* config.dropout, MAG dropout, summary_last_dropout (0 = eval) */
+  float grad_scale;
+  uint64_t seed;
+  const uint64_t* seed_dev;
+} magb200_xlnet_dims;
+
+size_t magb200_xlnet_workspace_bytes(const magb200_xlnet_dims* dims);
+int magb200_xlnet_refresh_operands(const magb200_xlnet_dims* dims, const int64_t* off, const float* params,
+                                   void* params16, void* stream);
+int magb200_xlnet_forward(const magb200_xlnet_dims* dims, const int64_t* off, const float* params, const void* params16,
+                          const int64_t* input_ids, const int64_t* token_type_ids, const int64_t* attention_mask,
+                          const float* visual, const float* acoustic, void* workspace, size_t workspace_bytes,
+                          float* logits, void* stream);
+int magb200_xlnet_backward(const magb200_xlnet_dims* dims, const int64_t* off, const float* params, const void* params16,
+                           const int64_t* input_ids, const int64_t* token_type_ids, const int64_t* attention_mask,
+                           void* workspace, size_t workspace_bytes, const float* dlogits_scaled, float* grads,
+                           void* stream);
+/* what: MAGB200_PEEK_MAG (MAG output), MAGB200_PEEK_LAYER_OUT (layer), MAGB200_PEEK_POOLED (summary) */
+int magb200_xlnet_peek(const magb200_xlnet_dims* dims, void* workspace, int what, int layer, void* out,
+                       size_t out_bytes, void* stream);
+
+/* XLNetRelativeAttention core (transformers 3.0.2 rel_attn_core + rel_shift_bnij, called through xlnet.py:374-385):
+ *   score[i][j] = ((q_i + r_w_bias).k_j + (q_i + r_r_bias).kr[j + S - i] + (q_i + r_s_bias).seg_embed[tt_i != tt_j]) / 8
+ *                 - 1e30 * (pad_j and i != j);  ctx = dropout(softmax(score)) v          S <= 64, head_dim 64
+ * kr16: projected relative positions [Bp][2S][heads*64] (Bp = 1 shared, or B when the position dropout differs per
+ * batch element). */
+int magb200_xlnet_rel_attn_fwd(const void* qkv16, const void* kr16, int Bp, const float* r_w_bias, const float* r_r_bias,
+                               const float* r_s_bias, const float* seg_embed, const int64_t* attention_mask,
+                               const int64_t* token_type_ids, int B, int S, int heads, int head_dim, float p, uint64_t seed,
+                               uint32_t site, void* ctx16, void* stream);
+/* dkr32 (fp32, [Bp][2S][heads*64]) and the four small parameter gradients are accumulated (+=); dqkv16 is written */
+int magb200_xlnet_rel_attn_bwd(const void* qkv16, const void* kr16, int Bp, const float* r_w_bias, const float* r_r_bias,
+                               const float* r_s_bias, const float* seg_embed, const int64_t* attention_mask,
+                               const int64_t* token_type_ids, const void* dctx16, int B, int S, int heads, int head_dim,
+                               float p, uint64_t seed, uint32_t site, float out_scale, void* dqkv16, float* dkr32,
+                               float* d_r_w_bias, float* d_r_r_bias, float* d_r_s_bias, float* d_seg_embed, void* stream);
+/* relative positional encoding (xlnet.py:93-146, attn_type "bi", bi_data False, clamp_len -1): pos16 [Bp][2S][768] */
+int magb200_xlnet_pos_emb(int S, int Bp, float p, uint64_t seed, uint32_t site, void* pos16, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
