@@ -326,6 +326,8 @@ def run_gpu_arm(args):
         if rank == 0:
             print(json.dumps({"profile_mode": True, "value_under_profiler": value, "ms_per_step": ms / args.steps,
                               "gpu_launches_per_step": int(launches_per_step)}), flush=True)
+        if world > 1:
+            finish_distributed(trainer, dist)
         return
 
     # ---------------- e2e: host batch -> pinned -> H2D -> step -> loss D2H, every step, through train_step()
@@ -378,8 +380,7 @@ def run_gpu_arm(args):
 
     if rank != 0:
         if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+            finish_distributed(trainer, dist)
         return
 
     # ---------------- rank 0 only: dominant-kernel roofline + CPU baseline
@@ -431,8 +432,20 @@ def run_gpu_arm(args):
     }
     print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        finish_distributed(trainer, dist)
+
+
+def finish_distributed(trainer, dist):
+    """Orderly exit of a multi-rank run: drop the captured graphs (they reference NCCL work), meet at a barrier,
+    then leave without tearing NCCL down from under them (destroy_process_group can block on captured
+    collectives); the process exit releases everything."""
+    import torch
+    trainer.release()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def main():

@@ -164,6 +164,15 @@ int magb200_bert_backward(const magb200_bert_dims* dims, const int64_t* off, con
                        attention_mask, workspace, workspace_bytes, dlogits_scaled, grads, ST);
 }
 
+int magb200_bert_backward_part(const magb200_bert_dims* dims, const int64_t* off, const float* params,
+                               const void* params16, const int64_t* input_ids, const int64_t* token_type_ids,
+                               const int64_t* attention_mask, void* workspace, size_t workspace_bytes,
+                               const float* dlogits_scaled, float* grads, int layer_hi, int layer_lo, int flags,
+                               void* stream) {
+  return bert_backward_part(*dims, off, params, reinterpret_cast<const __half*>(params16), input_ids, token_type_ids,
+                            attention_mask, workspace, workspace_bytes, dlogits_scaled, grads, layer_hi, layer_lo, flags, ST);
+}
+
 int magb200_bert_peek(const magb200_bert_dims* dims, void* workspace, int what, int layer, void* out, size_t out_bytes,
                       void* stream) {
   return bert_peek(*dims, workspace, what, layer, out, out_bytes, ST);

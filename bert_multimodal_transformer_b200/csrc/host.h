@@ -141,6 +141,9 @@ int bert_forward(const magb200_bert_dims& d, const int64_t* off, const float* P,
 int bert_backward(const magb200_bert_dims& d, const int64_t* off, const float* P, const __half* P16, const int64_t* ids,
                   const int64_t* tt, const int64_t* mask, void* workspace, size_t ws_bytes, const float* dlogits_scaled,
                   float* G, cudaStream_t st);
+int bert_backward_part(const magb200_bert_dims& d, const int64_t* off, const float* P, const __half* P16,
+                       const int64_t* ids, const int64_t* tt, const int64_t* mask, void* workspace, size_t ws_bytes,
+                       const float* dlogits_scaled, float* G, int layer_hi, int layer_lo, int flags, cudaStream_t st);
 int bert_peek(const magb200_bert_dims& d, void* workspace, int what, int layer, void* out, size_t out_bytes,
               cudaStream_t st);
 }  // namespace magb200

@@ -203,7 +203,17 @@ int bert_forward(const magb200_bert_dims& d, const int64_t* off, const float* P,
 int bert_backward(const magb200_bert_dims& d, const int64_t* off, const float* P, const __half* P16,
                   const int64_t* ids, const int64_t* tt, const int64_t* mask, void* workspace, size_t ws_bytes,
                   const float* dlogits_scaled, float* G, cudaStream_t st) {
+  return bert_backward_part(d, off, P, P16, ids, tt, mask, workspace, ws_bytes, dlogits_scaled, G, d.layers - 1, 0, 3, st);
+}
+
+// Backward in pieces so the caller can all-reduce finished gradient ranges while later pieces run:
+// layers layer_hi .. layer_lo (descending); flags bit 0 = run the head (classifier + pooler) first,
+// bit 1 = run the tail (MAG + embeddings) afterwards.  The running activation gradient lives in the workspace.
+int bert_backward_part(const magb200_bert_dims& d, const int64_t* off, const float* P, const __half* P16,
+                       const int64_t* ids, const int64_t* tt, const int64_t* mask, void* workspace, size_t ws_bytes,
+                       const float* dlogits_scaled, float* G, int layer_hi, int layer_lo, int flags, cudaStream_t st) {
   RUN(check_dims(d));
+  MAGB_REQUIRE(layer_hi < d.layers && layer_lo >= 0, "bert_backward_part: layer range [%d, %d] out of bounds", layer_lo, layer_hi);
   MAGB_REQUIRE(d.seq <= 128, "bert_backward: seq=%d > 128 not supported by the attention backward yet", d.seq);
   BertWs w = carve_ws(d, workspace);
   MAGB_REQUIRE(ws_bytes >= w.bytes, "bert_backward: workspace too small (%zu < %zu)", ws_bytes, w.bytes);
@@ -211,6 +221,7 @@ int bert_backward(const magb200_bert_dims& d, const int64_t* off, const float* P
   const float us = 1.0f / d.grad_scale;   // parameter gradients are stored unscaled
   const Seed sd{d.seed, d.seed_dev};
 
+  if (flags & 1) {
   // classifier + pooler                                                         bert.py:304-307, 231
   RUN(cls_bwd(dlogits_scaled, w.pooled32, P + off[MAGB200_OFF_CLS_W], B, d.num_labels, d.p_cls, sd, SITE_CLS,
               us, w.dpool16, G + off[MAGB200_OFF_CLS_W], G + off[MAGB200_OFF_CLS_B], st));
@@ -218,8 +229,9 @@ int bert_backward(const magb200_bert_dims& d, const int64_t* off, const float* P
   RUN(linear_dgrad(w.dpool16, H, P16 + off[MAGB200_OFF_POOL_W], H, B, H, H, EPI_STORE_F32, w.dy32, nullptr, S * H, st));
   RUN(linear_wgrad(w.dpool16, H, w.x16[d.layers], S * H, B, H, H, G + off[MAGB200_OFF_POOL_W], H, 1, us, st));
   RUN(colsum_f16(w.dpool16, B, H, us, G + off[MAGB200_OFF_POOL_B], st));
+  }
 
-  for (int l = d.layers - 1; l >= 0; --l) {
+  for (int l = layer_hi; l >= layer_lo; --l) {
     const int64_t* o = off + MAGB200_OFF_LAYER0 + (int64_t)l * MAGB200_OFF_PER_LAYER;
     LayerWs& L = w.layer[l];
     // BertOutput: LayerNorm(dropout(dense(g)) + a)
@@ -245,6 +257,7 @@ int bert_backward(const magb200_bert_dims& d, const int64_t* off, const float* P
     RUN(linear_dgrad(w.dqkv16, 3 * H, P16 + o[MAGB200_LOFF_QKV_W], H, T, H, 3 * H, EPI_STORE_F32, w.dy32, w.dy32, H, st));
   }
 
+  if (!(flags & 2)) return 0;
   // MAG (modeling.py:25-51)
   RUN(mag_tail_bwd(w.dy32, w.G32, w.emb32, P + off[MAGB200_OFF_MAG_LN_W], d.beta_shift, d.mag_ln_eps, d.p_mag, sd,
                    SITE_MAG, T, us, w.dG16, w.dr32, G + off[MAGB200_OFF_MAG_LN_W], G + off[MAGB200_OFF_MAG_LN_B],

@@ -138,6 +138,20 @@ class BertEngine:
                                           L.ptr(input_ids), L.ptr(token_type_ids), L.ptr(attention_mask), L.ptr(ws),
                                           ws.numel(), L.ptr(dlogits_scaled), L.ptr(grads), L.current_stream()))
 
+    def backward_part(self, dims, ws, input_ids, token_type_ids, attention_mask, dlogits_scaled, grads, layer_hi,
+                      layer_lo, flags):
+        L.check(L.load().magb200_bert_backward_part(byref(dims), self.offsets, L.ptr(self.flat), L.ptr(self.flat16),
+                                                    L.ptr(input_ids), L.ptr(token_type_ids), L.ptr(attention_mask),
+                                                    L.ptr(ws), ws.numel(), L.ptr(dlogits_scaled), L.ptr(grads), layer_hi,
+                                                    layer_lo, flags, L.current_stream()))
+
+    def layer_grad_range(self, lo, hi):
+        """[start, end) element range of the flat buffers covering encoder layers lo .. hi-1 (contiguous)."""
+        start = self.offsets[L.OFF_LAYER0 + L.OFF_PER_LAYER * lo + L.LOFF_QKV_W]
+        end = self.offsets[L.OFF_LAYER0 + L.OFF_PER_LAYER * hi + L.LOFF_QKV_W] if hi < self.layers \
+            else self.offsets[L.OFF_POOL_W]
+        return int(start), int(end)
+
     def peek(self, dims, ws, what, layer=0):
         lib = L.load()
         T = dims.batch * dims.seq

@@ -37,7 +37,8 @@ def linear_schedule(step: int, warmup: int, total: int) -> float:
 class MagBertTrainer:
     def __init__(self, model, batch_size: int, seq_len: int, lr: float = 1e-5, weight_decay: float = 0.01,
                  betas=(0.9, 0.999), eps: float = 1e-6, warmup_steps: int = 0, total_steps: int = 0,
-                 use_cuda_graph: bool = True, process_group=None, seed: int = 0, world_size: Optional[int] = None):
+                 use_cuda_graph: bool = True, process_group=None, seed: int = 0, world_size: Optional[int] = None,
+                 overlap_allreduce: bool = True):
         model._ensure_bound()
         self.model = model
         self.eng = model._engine      # BertEngine or XlnetEngine
@@ -96,6 +97,8 @@ class MagBertTrainer:
         self._train_graph_resident = None
         self._eval_graph_resident = None
         self.stream = torch.cuda.Stream(device=dev)
+        self.comm_stream = torch.cuda.Stream(device=dev)
+        self.overlap = overlap_allreduce
         eng.refresh_operands()
         self.kernel_launches_per_train_step = None
 
@@ -118,10 +121,13 @@ class MagBertTrainer:
                     i["acoustic"], self.logits)
         L.check(lib.magb200_mse_loss(L.ptr(self.logits), L.ptr(i["labels"]), self.B * eng.num_labels, eng.grad_scale,
                                      L.ptr(self.loss), L.ptr(self.dlogits), st))
-        eng.backward(self.train_dims, self.ws, i["input_ids"], i["token_type_ids"], i["attention_mask"], self.dlogits,
-                     self.grads)
-        if self.world > 1:
-            allreduce_sum_(self.grads, self.pg)
+        if self.world > 1 and self.overlap and hasattr(eng, "backward_part"):
+            self._backward_overlapped(i)
+        else:
+            eng.backward(self.train_dims, self.ws, i["input_ids"], i["token_type_ids"], i["attention_mask"], self.dlogits,
+                         self.grads)
+            if self.world > 1:
+                allreduce_sum_(self.grads, self.pg)
         L.check(lib.magb200_adamw_step(L.ptr(eng.flat), L.ptr(self.grads), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq),
                                        L.ptr(eng.flat16), L.ptr(self.decay), eng.layout.total, self.lr, self.betas[0],
                                        self.betas[1], self.eps, self.wd, 1, grad_unscale(self.world), 1, L.ptr(self.dev_hyper),
@@ -129,6 +135,43 @@ class MagBertTrainer:
         eng.after_optimizer_step()
         if transfers:
             self.host_loss[slot].copy_(self.loss, non_blocking=True)
+
+    def _backward_overlapped(self, i):
+        """Backward in 3 pieces; the gradient range of each finished group of layers is all-reduced on a side
+        stream while the next piece computes (bucketed overlap).  The order of the flat buffer
+        is [embeddings | layer 0 .. L-1 | pooler, MAG, classifier], so a group of layers is one contiguous slice."""
+        eng = self.eng
+        main = torch.cuda.current_stream(self.dev)
+        side = self.comm_stream
+        Ln = eng.layers
+        cuts = sorted({Ln, (2 * Ln) // 3, Ln // 3, 0}, reverse=True)          # e.g. 12, 8, 4, 0
+        groups = [(cuts[k + 1], cuts[k]) for k in range(len(cuts) - 1)]       # [(8,12), (4,8), (0,4)]
+        args = (self.train_dims, self.ws, i["input_ids"], i["token_type_ids"], i["attention_mask"], self.dlogits,
+                self.grads)
+        for gi, (lo, hi) in enumerate(groups):
+            last = gi == len(groups) - 1
+            eng.backward_part(*args, hi - 1, lo, (1 if gi == 0 else 0) | (2 if last else 0))
+            if not last:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+                s, e = eng.layer_grad_range(lo, hi)
+                with torch.cuda.stream(side):
+                    allreduce_sum_(self.grads[s:e], self.pg)
+        # what is left: embeddings + the first group of layers, and pooler / MAG / classifier at the end
+        lo0, hi0 = groups[-1]
+        s, e = eng.layer_grad_range(lo0, hi0)
+        allreduce_sum_(self.grads[:e], self.pg)
+        allreduce_sum_(self.grads[int(eng.offsets[L.OFF_POOL_W]):], self.pg)
+        main.wait_stream(side)
+
+    def release(self):
+        """Drop the captured graphs (they hold NCCL work when world > 1) -- call before destroying the process group."""
+        self._train_graph = [None] * self.NSLOT
+        self._eval_graph = [None] * self.NSLOT
+        self._train_graph_resident = None
+        self._eval_graph_resident = None
+        torch.cuda.synchronize(self.dev)
 
     def _eval_body(self, transfers=True, slot=0):
         eng = self.eng

@@ -204,6 +204,14 @@ int magb200_bert_backward(const magb200_bert_dims* dims, const int64_t* off, con
                           const int64_t* input_ids, const int64_t* token_type_ids, const int64_t* attention_mask,
                           void* workspace, size_t workspace_bytes, const float* dlogits_scaled, float* grads,
                           void* stream);
+/* The same backward in pieces, so a data-parallel caller can all-reduce the gradient range of finished layers
+ * while the next piece runs: layers layer_hi .. layer_lo (descending); flags bit 0 = classifier + pooler first,
+ * bit 1 = MAG + embeddings last.  magb200_bert_backward == part(layers-1, 0, 3). */
+int magb200_bert_backward_part(const magb200_bert_dims* dims, const int64_t* off, const float* params,
+                               const void* params16, const int64_t* input_ids, const int64_t* token_type_ids,
+                               const int64_t* attention_mask, void* workspace, size_t workspace_bytes,
+                               const float* dlogits_scaled, float* grads, int layer_hi, int layer_lo, int flags,
+                               void* stream);
 /* copy a saved activation out of the workspace (tests): MAGB200_PEEK_* */
 int magb200_bert_peek(const magb200_bert_dims* dims, void* workspace, int what, int layer, void* out, size_t out_bytes,
                       void* stream);

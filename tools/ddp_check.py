@@ -17,7 +17,7 @@ from bert_multimodal_transformer_b200.parallel import shard_batch
 from bert_multimodal_transformer_b200.trainer import MagBertTrainer
 from oracle import inputs as gen, weights
 
-LAYERS, GLOBAL_B, STEPS = 4, 16 * world, 3
+LAYERS, GLOBAL_B, STEPS = 4, 16 * world, 1
 
 def make():
     class MC: beta_shift, dropout_prob = 1.0, 0.0
@@ -32,24 +32,29 @@ mine = shard_batch(full, rank, world)
 args = lambda b: (b["input_ids"], b["visual"], b["acoustic"], b["attention_mask"], b["token_type_ids"], b["labels"])
 
 model = make()
-tr = MagBertTrainer(model, GLOBAL_B // world, 50, lr=1e-3, weight_decay=0.01, total_steps=0, use_cuda_graph=True)
+tr = MagBertTrainer(model, GLOBAL_B // world, 50, lr=1e-4, weight_decay=0.01, total_steps=0, use_cuda_graph=True)
 losses = [tr.train_step(*args(mine)) for _ in range(STEPS)]
 torch.cuda.synchronize()
 ok = True
 if rank == 0:
     ref_model = make()
-    ref = MagBertTrainer(ref_model, GLOBAL_B, 50, lr=1e-3, weight_decay=0.01, total_steps=0, use_cuda_graph=False,
+    ref = MagBertTrainer(ref_model, GLOBAL_B, 50, lr=1e-4, weight_decay=0.01, total_steps=0, use_cuda_graph=False,
                          world_size=1)
     ref_losses = [ref.train_step(*args(full)) for _ in range(STEPS)]
     torch.cuda.synchronize()
-    a, b = model._engine.flat, ref_model._engine.flat
-    num = (a - b).norm().item(); den = (b - torch.zeros_like(b)).norm().item()
-    upd = (b - MagBertTrainer.__mro__[0].__name__ and b).norm().item()
-    init = make()._engine if False else None
-    drift = (a - b).abs().max().item()
-    print(json.dumps({"world": world, "max_abs_param_diff": drift, "rel_param_diff": num / den,
+    # Adam's update is invariant to the gradient scale, so compare the first moment after one step instead:
+    # exp_avg = (1 - beta1) * (mean gradient over the GLOBAL batch); a sum-instead-of-mean or a slice missing from
+    # the all-reduce shows up as a factor `world` / a zero block.
+    a, b = tr.exp_avg, ref.exp_avg
+    rel = ((a - b).norm() / b.norm()).item()
+    lay = model._engine.layout
+    worst = max((((lay.view(a, n) - lay.view(b, n)).norm() / (lay.view(b, n).norm() + 1e-20)).item(), n)
+                for n in model._engine.order if lay.view(b, n).norm().item() > 1e-4 * b.norm().item())  # key biases have zero true gradient
+    pa, pb = model._engine.flat, ref_model._engine.flat
+    print(json.dumps({"world": world, "rel_first_moment_diff": rel, "worst_tensor": worst,
+                      "rel_param_diff": ((pa - pb).norm() / pb.norm()).item(),
                       "rank0_local_losses": losses, "single_process_losses": ref_losses}))
-    ok = drift < 2e-4      # lr 1e-3 Adam steps are ~1e-3 each: a wrong reduction shows up as >1e-3
+    ok = rel < 1e-3 and worst[0] < 2e-2
 # every rank must hold identical parameters after the all-reduced steps
 chk = model._engine.flat.double().sum().reshape(1)
 lo, hi = chk.clone(), chk.clone()
@@ -58,6 +63,10 @@ if rank == 0:
     print("replica checksum spread", float(hi - lo))
     ok = ok and float(hi - lo) == 0.0
     print("DDP_CHECK", "PASS" if ok else "FAIL")
+flag = torch.tensor([1 if ok else 0], device="cuda")
+dist.broadcast(flag, 0)
+tr.release()
 dist.barrier()
-dist.destroy_process_group()
-sys.exit(0 if ok else 1)
+torch.cuda.synchronize()
+sys.stdout.flush()
+os._exit(0 if int(flag.item()) == 1 else 1)

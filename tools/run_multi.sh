@@ -1,0 +1,13 @@
+#!/bin/bash
+mkdir -p gpurun_out
+N=${1:-2}
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29601 tools/ddp_check.py > gpurun_out/ddp_check_$N.log 2>&1; echo "ddp_check exit=$?"
+grep -E "DDP_CHECK|max_abs|spread|Error|error" gpurun_out/ddp_check_$N.log | cut -c1-600 | tail -8
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29602 bench.py --gpus $N --steps 60 --warmup 5 --no-cpu-baseline > gpurun_out/bench_n$N.log 2>&1; echo "bench exit=$?"
+grep '"metric"' gpurun_out/bench_n$N.log | python -c "
+import json,sys
+try:
+    d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('value','n_gpus','ms_per_step')}, d['e2e']['value'], d['eval_forward']['value'])
+except Exception as e: print('parse fail', e)
+"
+tail -3 gpurun_out/bench_n$N.log | cut -c1-300
