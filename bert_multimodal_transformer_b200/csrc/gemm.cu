@@ -86,34 +86,113 @@ static int get_tensor_map(CUtensorMap* out, const void* ptr, int dtype, uint64_t
   return 0;
 }
 
-template <int EB, bool A_MN, bool B_MN, int BN, int STAGES>
+template <int EB, bool A_MN, bool B_MN, int BN, int STAGES, int CL>
 static int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, dim3 grid, cudaStream_t st) {
   using SM = GemmSmem<EB, A_MN, B_MN, BN, STAGES>;
-  auto kern = gemm_tcgen05_kernel<EB, A_MN, B_MN, BN, STAGES>;
+  auto kern = gemm_tcgen05_kernel<EB, A_MN, B_MN, BN, STAGES, CL>;
   static bool configured = false;
   if (!configured) {
     MAGB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
     configured = true;
   }
-  kern<<<grid, 192, SM::TOTAL, st>>>(ta, tb, g);
+  if (CL == 1) {
+    kern<<<grid, 192, SM::TOTAL, st>>>(ta, tb, g);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = SM::TOTAL; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    MAGB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, g));
+  }
   MAGB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
 }
 
-template <int EB, int BN, int STAGES>
+template <int EB, int BN, int STAGES, int CL>
 static int launch_majors(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g,
                          dim3 grid, cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch_variant<EB, false, false, BN, STAGES>(ta, tb, g, grid, st);
-  if (!a_mn && b_mn) return launch_variant<EB, false, true, BN, STAGES>(ta, tb, g, grid, st);
-  if (a_mn && !b_mn) return launch_variant<EB, true, false, BN, STAGES>(ta, tb, g, grid, st);
-  return launch_variant<EB, true, true, BN, STAGES>(ta, tb, g, grid, st);
+  if (!a_mn && !b_mn) return launch_variant<EB, false, false, BN, STAGES, CL>(ta, tb, g, grid, st);
+  if (!a_mn && b_mn) return launch_variant<EB, false, true, BN, STAGES, CL>(ta, tb, g, grid, st);
+  if (a_mn && !b_mn) return launch_variant<EB, true, false, BN, STAGES, CL>(ta, tb, g, grid, st);
+  return launch_variant<EB, true, true, BN, STAGES, CL>(ta, tb, g, grid, st);
 }
 
 // debug/tuning hooks (tools/gemm_tune.py): trace buffer and tile-configuration override
 static unsigned long long* g_trace = nullptr;
 static int g_cfg = 0;
-void gemm_set_debug(unsigned long long* trace, int cfg) { g_trace = trace; g_cfg = cfg; }
+static int g_dbg = 0;
+void gemm_set_debug(unsigned long long* trace, int cfg) { g_trace = trace; g_cfg = cfg % 100; g_dbg = cfg / 100; }
+
+// ---------------------------------------------------------------------------------------------
+// 2-CTA (cta_group::2) path
+template <bool A_MN, bool B_MN, int BN, int STAGES>
+static int launch2_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, dim3 grid, cudaStream_t st) {
+  using SM = Gemm2Smem<BN, STAGES>;
+  auto kern = gemm2_tcgen05_kernel<A_MN, B_MN, BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    MAGB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = SM::TOTAL; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  MAGB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, g));
+  MAGB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+template <int BN, int STAGES>
+static int launch2_majors(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, dim3 grid,
+                          cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch2_variant<false, false, BN, STAGES>(ta, tb, g, grid, st);
+  if (!a_mn && b_mn) return launch2_variant<false, true, BN, STAGES>(ta, tb, g, grid, st);
+  if (a_mn && !b_mn) return launch2_variant<true, false, BN, STAGES>(ta, tb, g, grid, st);
+  return launch2_variant<true, true, BN, STAGES>(ta, tb, g, grid, st);
+}
+
+static int gemm_launch_2cta(const GemmProblem& p, int BN, cudaStream_t st) {
+  const int BK = 64, ATOM = 64, BM = 128;
+  CUtensorMap ta, tb;
+  int rc;
+  if (!p.a_mn) rc = get_tensor_map(&ta, p.A, p.a_dtype, p.K, p.M, p.lda, BK, BM);
+  else rc = get_tensor_map(&ta, p.A, p.a_dtype, p.M, p.K, p.lda, ATOM, BK);
+  if (rc) return rc;
+  if (!p.b_mn) rc = get_tensor_map(&tb, p.B, p.b_dtype, p.K, p.N, p.ldb, BK, BN / 2);   // each CTA loads half the N tile
+  else rc = get_tensor_map(&tb, p.B, p.b_dtype, p.N, p.K, p.ldb, ATOM, BK);
+  if (rc) return rc;
+  GemmArgs g;
+  g.M = p.M; g.N = p.N; g.K = p.K;
+  g.kb_total = (p.K + BK - 1) / BK;
+  int splits = p.splits < 1 ? 1 : p.splits;
+  if (splits > g.kb_total) splits = g.kb_total;
+  g.kb_per_split = (g.kb_total + splits - 1) / splits;
+  splits = (g.kb_total + g.kb_per_split - 1) / g.kb_per_split;
+  MAGB_REQUIRE(splits == 1 || p.epi == EPI_ATOMIC_F32, "gemm: split-K requires the atomic epilogue");
+  g.n_split = 0x7fffffff; g.kb_start_hi = 0;
+  g.epi = p.epi; g.bias = p.bias; g.out0 = p.out0; g.out1 = p.out1; g.aux = p.aux; g.ldo = p.ldo; g.alpha = p.alpha;
+  const uint32_t fmt = p.a_dtype == DT_BF16 ? 1u : 0u;
+  g.idesc = make_idesc(fmt, fmt, p.a_mn, p.b_mn, 256, BN);     // the pair's UMMA: M = 256
+  g.trace = nullptr;
+  g.dbg = 0;
+  g.drop_thresh = 0; g.drop_scale = 1.f; g.drop_site = p.drop_site; g.drop_seed = p.drop_seed.value;
+  g.drop_seed_ptr = reinterpret_cast<const unsigned long long*>(p.drop_seed.ptr);
+  if (p.drop_p > 0.f) {
+    const double t = (double)p.drop_p * 4294967296.0;
+    g.drop_thresh = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
+    g.drop_scale = 1.0f / (1.0f - p.drop_p);
+  }
+  const int m_pairs = (p.M + 2 * BM - 1) / (2 * BM);
+  dim3 grid(2 * m_pairs, (p.N + BN - 1) / BN, splits);      // x = M tiles (pair-adjacent), y = N tiles
+  if (BN == 256) return launch2_majors<256, 5>(p.a_mn, p.b_mn, ta, tb, g, grid, st);
+  return launch2_majors<128, 4>(p.a_mn, p.b_mn, ta, tb, g, grid, st);
+}
 
 int gemm_launch(const GemmProblem& p, cudaStream_t st) {
   MAGB_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem %dx%dx%d", p.M, p.N, p.K);
@@ -124,13 +203,30 @@ int gemm_launch(const GemmProblem& p, cudaStream_t st) {
   MAGB_REQUIRE(!(a32 && (p.a_mn || p.b_mn)), "gemm: tf32 operands must be K-major");
   const int EB = a32 ? 4 : 2;
   const int BK = 128 / EB, ATOM = 128 / EB, BM = 128;
-  const int BN = (g_cfg >= 3) ? 256 : 128;
+  const int BN = (g_cfg == 3 || g_cfg == 4) ? 256 : 128;
   MAGB_REQUIRE(p.N % 32 == 0, "gemm: N=%d must be a multiple of 32", p.N);
   MAGB_REQUIRE(p.ldo % 8 == 0, "gemm: ldo=%d must be a multiple of 8", p.ldo);
+  // 2-CTA (cta_group::2) pair tiles.  Measured on B200 (profiles/r01_gemm_modes.txt, r01_gemm_tile_sweep.txt):
+  // the 1-CTA 128x128 SS-mode main loop is shared-memory-bandwidth bound (UMMA operand reads 128 B/clk + TMA fill
+  // 128 B/clk against 128 B/clk of SMEM), the pair tile halves the per-SM B traffic.  At these problem sizes
+  // (M = 2400) 256x128 pair tiles win 7-9 % on the long-K GEMMs (K >= 2048: FFN-out, its dgrad, the FFN/QKV
+  // wgrads); for K = 768 the epilogue and tile quantisation dominate and the 1-CTA kernel with two co-resident
+  // CTAs per SM is as fast.  cfg 5 forces 1-CTA, cfg 7 forces 256x128 pairs, cfg 8 256x256 pairs where N allows.
+  const bool pair_ok = EB == 2 && p.n_split <= 0 && p.N % 128 == 0;
+  if (pair_ok && (g_cfg == 7 || g_cfg == 8 || (g_cfg == 0 && p.K >= 2048))) {
+    const int bn2 = (g_cfg == 8 && p.N % 256 == 0 && p.N >= 1024) ? 256 : 128;
+    return gemm_launch_2cta(p, bn2, st);
+  }
 
+  // cluster of 2 CTAs along N sharing (multicasting) the A tile: needs an even number of N tiles and identical K
+  // ranges in both CTAs (no n_split).  Measured on B200 (profiles/r01_gemm_multicast.txt): correct, but no faster --
+  // the main loop is bound by bytes ARRIVING per SM (~56-84 B/clk), which multicast does not reduce; it stays
+  // opt-in (cfg 6) until the 2-CTA (cta_group::2) tile halves the per-SM B traffic.
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const bool cluster2 = (EB == 2) && (BN == 128) && (n_tiles % 2 == 0) && (p.n_split <= 0) && (g_cfg == 6);
   CUtensorMap ta, tb;
   int rc;
-  if (!p.a_mn) rc = get_tensor_map(&ta, p.A, p.a_dtype, p.K, p.M, p.lda, BK, BM);
+  if (!p.a_mn) rc = get_tensor_map(&ta, p.A, p.a_dtype, p.K, p.M, p.lda, BK, cluster2 ? BM / 2 : BM);
   else rc = get_tensor_map(&ta, p.A, p.a_dtype, p.M, p.K, p.lda, ATOM, BK);
   if (rc) return rc;
   if (!p.b_mn) rc = get_tensor_map(&tb, p.B, p.b_dtype, p.K, p.N, p.ldb, BK, BN);
@@ -156,6 +252,7 @@ int gemm_launch(const GemmProblem& p, cudaStream_t st) {
   const uint32_t bf = p.b_dtype == DT_F32 ? 2u : (p.b_dtype == DT_BF16 ? 1u : 0u);
   g.idesc = make_idesc(af, bf, p.a_mn, p.b_mn, BM, BN);
   g.trace = g_trace;
+  g.dbg = g_dbg;
   g.drop_thresh = 0; g.drop_scale = 1.f; g.drop_site = p.drop_site; g.drop_seed = p.drop_seed.value;
   g.drop_seed_ptr = reinterpret_cast<const unsigned long long*>(p.drop_seed.ptr);
   if (p.drop_p > 0.f) {
@@ -168,15 +265,15 @@ int gemm_launch(const GemmProblem& p, cudaStream_t st) {
 
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, splits);
   if (EB == 2) {
+    if (cluster2) return launch_majors<2, 128, 3, 2>(p.a_mn, p.b_mn, ta, tb, g, grid, st);
     switch (g_cfg) {
-      case 1: return launch_majors<2, 128, 4>(p.a_mn, p.b_mn, ta, tb, g, grid, st);
-      case 2: return launch_majors<2, 128, 6>(p.a_mn, p.b_mn, ta, tb, g, grid, st);
-      case 3: return launch_majors<2, 256, 3>(p.a_mn, p.b_mn, ta, tb, g, grid, st);
-      case 4: return launch_majors<2, 256, 4>(p.a_mn, p.b_mn, ta, tb, g, grid, st);
-      default: return launch_majors<2, 128, 3>(p.a_mn, p.b_mn, ta, tb, g, grid, st);
+      case 1: return launch_majors<2, 128, 4, 1>(p.a_mn, p.b_mn, ta, tb, g, grid, st);
+      case 3: return launch_majors<2, 256, 3, 1>(p.a_mn, p.b_mn, ta, tb, g, grid, st);
+      case 4: return launch_majors<2, 256, 4, 1>(p.a_mn, p.b_mn, ta, tb, g, grid, st);
+      default: return launch_majors<2, 128, 3, 1>(p.a_mn, p.b_mn, ta, tb, g, grid, st);
     }
   }
-  return launch_majors<4, 128, 3>(p.a_mn, p.b_mn, ta, tb, g, grid, st);
+  return launch_majors<4, 128, 3, 1>(p.a_mn, p.b_mn, ta, tb, g, grid, st);
 }
 
 }  // namespace magb200

@@ -53,6 +53,8 @@ struct GemmArgs {
   uint32_t drop_site;
   unsigned long long drop_seed;
   const unsigned long long* drop_seed_ptr;
+  int dbg;   // measurement modes (results are garbage): 1 = MMA issue without waiting for operands,
+             // 2 = operand delivery only (no MMA; the consumer releases each stage as soon as it lands)
 };
 
 template <int EB>
@@ -109,15 +111,31 @@ __device__ __forceinline__ void stage_in(uint8_t* stg, int pitch, const uint8_t*
         *reinterpret_cast<uint4*>(stg + r * pitch + c) = *reinterpret_cast<const uint4*>(gsrc + (size_t)r * gpitch + c);
   }
 }
-// staging -> global, coalesced store (or fp32 reduction when `atomic`)
+// staging -> global, coalesced store (or fp32 reduction when `atomic`).  Four row-slices are read from shared
+// memory before their stores are issued: a store-after-load chain per slice (what a naive loop compiles to with
+// volatile asm stores) reached 16 B/clk/SM, the batched form reaches the ~35 B/clk/SM the store path sustains
+// (tools/micro/store_bw.cu).
 __device__ __forceinline__ void stage_out(const uint8_t* stg, int pitch, uint8_t* __restrict__ gdst, size_t gpitch,
                                           int rows, int rowbytes, int lane, bool atomic) {
   const int lpr = rowbytes >> 4;
   const int rpi = lpr <= 32 ? 32 / lpr : 1;
   const int lr = lpr <= 32 ? lane / lpr : 0;
   const int lc0 = lpr <= 32 ? (lane % lpr) << 4 : lane << 4;
-  for (int r = lr; r < rows; r += rpi) {
-    for (int c = lc0; c < rowbytes; c += 512) {
+  for (int c = lc0; c < rowbytes; c += 512) {
+    int r = lr;
+    for (; r + 3 * rpi < rows; r += 4 * rpi) {
+      uint4 v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[q] = *reinterpret_cast<const uint4*>(stg + (r + q * rpi) * pitch + c);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint8_t* d = gdst + (size_t)(r + q * rpi) * gpitch + c;
+        if (!atomic) st_global_v4(d, v[q].x, v[q].y, v[q].z, v[q].w);
+        else red_add_v4(reinterpret_cast<float*>(d), __uint_as_float(v[q].x), __uint_as_float(v[q].y),
+                        __uint_as_float(v[q].z), __uint_as_float(v[q].w));
+      }
+    }
+    for (; r < rows; r += rpi) {
       const uint4 v = *reinterpret_cast<const uint4*>(stg + r * pitch + c);
       uint8_t* d = gdst + (size_t)r * gpitch + c;
       if (!atomic) st_global_v4(d, v.x, v.y, v.z, v.w);
@@ -189,13 +207,15 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& g, uint32_t t
              (size_t)g.ldo * es, rows, ncols * es, lane);
   }
   __syncwarp();
-  const int npass = (epi == EPI_GELU_F16 && g.out1 != nullptr) || epi == EPI_STORE_F32_F16 ? 2 : 1;
+  // GELU with both outputs (g16 and the pre-activation u16 the backward needs): both are fp16, so the two staged
+  // tiles fit side by side in the warp's region (2 x BN*2 B <= BN*4 B per row) and one TMEM pass produces both.
+  const bool dual16 = (epi == EPI_GELU_F16 && g.out1 != nullptr);
+  const int npass = epi == EPI_STORE_F32_F16 ? 2 : 1;
   for (int pass = 0; pass < npass; ++pass) {
     // which output this pass produces, and its element size
     int es = 4;
     void* out = g.out0;
-    if (epi == EPI_STORE_F16 || epi == EPI_STORE_BF16 || epi == EPI_DGELU_F16) es = 2;
-    if (epi == EPI_GELU_F16) { es = 2; out = (npass == 2 && pass == 0) ? g.out1 : g.out0; }
+    if (epi == EPI_STORE_F16 || epi == EPI_STORE_BF16 || epi == EPI_DGELU_F16 || epi == EPI_GELU_F16) es = 2;
     if (epi == EPI_STORE_F32_F16) { es = pass == 0 ? 4 : 2; out = pass == 0 ? g.out0 : g.out1; }
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
@@ -237,11 +257,10 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& g, uint32_t t
           row_write_16<true>(myrow, c, v);
           break;
         case EPI_GELU_F16:
-          if (!(npass == 2 && pass == 0)) {
+          if (dual16) row_write_16<false>(myrow + BN * 2, c, v);      // pre-activation, upper half of the row
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-            if (g.drop_thresh != 0) epi_dropout(g, m_base + lane, n0 + c * 32, v);
-          }
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          if (g.drop_thresh != 0) epi_dropout(g, m_base + lane, n0 + c * 32, v);
           row_write_16<false>(myrow, c, v);
           break;
         case EPI_DGELU_F16: {
@@ -265,9 +284,13 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& g, uint32_t t
     }
     __syncwarp();
     if (tr) tr[56] = clock64();
-    if (live)
+    if (live) {
       stage_out(stg, PITCH, reinterpret_cast<uint8_t*>(out) + ((size_t)m_base * g.ldo + n0) * es, (size_t)g.ldo * es,
                 rows, ncols * es, lane, epi == EPI_ATOMIC_F32);
+      if (dual16)
+        stage_out(stg + BN * 2, PITCH, reinterpret_cast<uint8_t*>(g.out1) + ((size_t)m_base * g.ldo + n0) * 2,
+                  (size_t)g.ldo * 2, rows, ncols * 2, lane, false);
+    }
     __syncwarp();
   }
 }
@@ -282,7 +305,12 @@ struct GemmSmem {
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
 };
 
-template <int EB, bool A_MN, bool B_MN, int BN, int STAGES>
+// CL = cluster size along N (1 or 2).  With CL = 2 the two CTAs of a cluster compute adjacent N tiles of the same
+// M tile and SHARE the A operand: each loads half of the A tile and multicasts it to both (per-SM TMA delivery
+// is the main-loop limiter -- profiles/r01_gemm_pipeline_trace.txt -- so A costs each SM 8 KB instead of 16 KB
+// per K block).  A stage is then released only when BOTH CTAs' MMAs have read it (empty barriers count CL
+// arrivals, tcgen05.commit multicast).
+template <int EB, bool A_MN, bool B_MN, int BN, int STAGES, int CL>
 __global__ void __launch_bounds__(192, 2)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
   using T = GemmTile<EB>;
@@ -317,7 +345,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) {
         mbar_init(&full_bar[s], 1);
-        mbar_init(&empty_bar[s], 1);
+        mbar_init(&empty_bar[s], CL);
       }
       mbar_init(tmem_full_bar, 1);
       fence_barrier_init();
@@ -328,65 +356,102 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();   // peer barriers are initialised before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1);
   if (tr && threadIdx.x == 0) tr[1] = clock64();
 
+  // Both single-thread loops walk the stage ring with the stage index as a compile-time constant (outer loop over
+  // ring revolutions, inner loop unrolled over STAGES): shared-memory addresses, barrier addresses and the UMMA
+  // descriptors are then "base + constant", one uniform add each, instead of a dependent chain per instruction.
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      for (int it = 0; it < num_kb; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full_bar[s], SM::STAGE_BYTES);
-        uint8_t* a_dst = smem + s * SM::STAGE_BYTES;
-        uint8_t* b_dst = a_dst + SM::A_BYTES;
-        const int k0 = (kb_begin + it) * T::BK;
-        if constexpr (!A_MN) {
-          tma_load_2d(a_dst, &tmA, &full_bar[s], k0, m0);
-        } else {
+      for (int base = 0; base < num_kb; base += STAGES) {
+        const uint32_t ph = (base / STAGES) & 1;
 #pragma unroll
-          for (int i = 0; i < T::BM / T::ATOM; ++i)
-            tma_load_2d(a_dst + i * (T::BK * 128), &tmA, &full_bar[s], m0 + i * T::ATOM, k0);
-        }
-        if constexpr (!B_MN) {
-          tma_load_2d(b_dst, &tmB, &full_bar[s], k0, n0);
-        } else {
+        for (int s = 0; s < STAGES; ++s) {
+          if (base + s < num_kb) {
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            mbar_arrive_expect_tx(&full_bar[s], SM::STAGE_BYTES);
+            uint8_t* a_dst = smem + s * SM::STAGE_BYTES;
+            uint8_t* b_dst = a_dst + SM::A_BYTES;
+            const int k0 = (kb_begin + base + s) * T::BK;
+            if constexpr (CL == 1) {
+              if constexpr (!A_MN) {
+                tma_load_2d(a_dst, &tmA, &full_bar[s], k0, m0);
+              } else {
 #pragma unroll
-          for (int i = 0; i < BN / T::ATOM; ++i)
-            tma_load_2d(b_dst + i * (T::BK * 128), &tmB, &full_bar[s], n0 + i * T::ATOM, k0);
+                for (int i = 0; i < T::BM / T::ATOM; ++i)
+                  tma_load_2d(a_dst + i * (T::BK * 128), &tmA, &full_bar[s], m0 + i * T::ATOM, k0);
+              }
+            } else {
+              // this CTA's share of the A tile (rows / MN atoms crank*BM/CL ...), delivered to every CTA of the cluster
+              constexpr int SHARE = T::BM / CL;   // A rows per CTA
+              if constexpr (!A_MN) {
+                tma_load_2d_mc(a_dst + crank * (SHARE * 128), &tmA, &full_bar[s], k0, m0 + crank * SHARE, kMask);
+              } else {
+#pragma unroll
+                for (int i = 0; i < SHARE / T::ATOM; ++i) {
+                  const int atom = crank * (SHARE / T::ATOM) + i;
+                  tma_load_2d_mc(a_dst + atom * (T::BK * 128), &tmA, &full_bar[s], m0 + atom * T::ATOM, k0, kMask);
+                }
+              }
+            }
+            if constexpr (!B_MN) {
+              tma_load_2d(b_dst, &tmB, &full_bar[s], k0, n0);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BN / T::ATOM; ++i)
+                tma_load_2d(b_dst + i * (T::BK * 128), &tmB, &full_bar[s], n0 + i * T::ATOM, k0);
+            }
+            if (tr && base + s < 16) tr[2 + base + s] = clock64();
+          }
         }
-        if (tr && it < 16) tr[2 + it] = clock64();
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      for (int it = 0; it < num_kb; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        if (tr && it < 16) tr[20 + it] = clock64();
-        const uint32_t a_base = smem_u32(smem + s * SM::STAGE_BYTES);
-        const uint32_t b_base = a_base + SM::A_BYTES;
+      const uint32_t sb16 = smem_u32(smem) >> 4;
+      const uint32_t dhi = smem_desc_hi_sw128(1024);
+      // K-major : 8-row groups 1024 B apart (SBO); K advances 32 B inside the 128-B swizzle row.
+      // MN-major: 64-element (128 B) MN atoms BK*128 B apart (LBO), 8-K-row groups 1024 B apart (SBO);
+      //           K advances UK rows = UK*128 B.
+      constexpr uint32_t A_LBO = A_MN ? T::BK * 128 : 0, B_LBO = B_MN ? T::BK * 128 : 0;
+      constexpr uint32_t A_KSTEP = A_MN ? T::UK * 128 : 32, B_KSTEP = B_MN ? T::UK * 128 : 32;
+      for (int base = 0; base < num_kb; base += STAGES) {
+        const uint32_t ph = (base / STAGES) & 1;
 #pragma unroll
-        for (int k = 0; k < T::BK / T::UK; ++k) {
-          // K-major : 8-row groups 1024 B apart (SBO); K advances 32 B inside the 128-B swizzle row.
-          // MN-major: 64-element (128 B) MN atoms BK*128 B apart (LBO), 8-K-row groups 1024 B apart
-          //           (SBO); K advances UK rows = UK*128 B.
-          const uint64_t adesc = A_MN ? make_smem_desc_sw128(a_base + k * T::UK * 128, T::BK * 128, 1024)
-                                      : make_smem_desc_sw128(a_base + k * 32, 0, 1024);
-          const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_base + k * T::UK * 128, T::BK * 128, 1024)
-                                      : make_smem_desc_sw128(b_base + k * 32, 0, 1024);
-          if constexpr (EB == 2) tc_mma_f16(tmem_base, adesc, bdesc, g.idesc, (it | k) != 0);
-          else tc_mma_tf32(tmem_base, adesc, bdesc, g.idesc, (it | k) != 0);
+        for (int s = 0; s < STAGES; ++s) {
+          if (base + s < num_kb) {
+            if (g.dbg != 1) mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            if (tr && base + s < 16) tr[20 + base + s] = clock64();
+            if (g.dbg == 2) {
+              mbar_arrive(&empty_bar[s]);
+              if (tr && base + s < 16) tr[40 + base + s] = clock64();
+              continue;
+            }
+#pragma unroll
+            for (int k = 0; k < T::BK / T::UK; ++k) {
+              const uint64_t adesc = smem_desc_from(dhi, sb16 + ((s * SM::STAGE_BYTES + k * A_KSTEP) >> 4), A_LBO);
+              const uint64_t bdesc =
+                  smem_desc_from(dhi, sb16 + ((s * SM::STAGE_BYTES + SM::A_BYTES + k * B_KSTEP) >> 4), B_LBO);
+              const uint32_t acc = (s | k) != 0 ? 1u : (uint32_t)(base != 0);
+              if constexpr (EB == 2) tc_mma_f16(tmem_base, adesc, bdesc, g.idesc, acc);
+              else tc_mma_tf32(tmem_base, adesc, bdesc, g.idesc, acc);
+            }
+            if constexpr (CL == 1) tc_commit(&empty_bar[s]);  // smem slot reusable once these MMAs have read it
+            else tc_commit_mc(&empty_bar[s], kMask);          // ... in every CTA that multicasts into it
+            if (tr && base + s < 16) tr[40 + base + s] = clock64();
+          }
         }
-        tc_commit(&empty_bar[s]);  // smem slot reusable once these MMAs have read it
-        if (tr && it < 16) tr[40 + it] = clock64();
       }
-      tc_commit(tmem_full_bar);    // accumulator complete
+      if (g.dbg == 2) mbar_arrive(tmem_full_bar);
+      else tc_commit(tmem_full_bar);    // accumulator complete
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
@@ -404,7 +469,151 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, BN);
+  if constexpr (CL > 1) cluster_sync_all();   // do not exit while the peer can still signal our barriers
   if (tr && threadIdx.x == 0) tr[62] = clock64();
+}
+
+
+// ================================================================================================
+// 2-CTA kernel (tcgen05 cta_group::2): a cluster of two CTAs on one SM pair computes a 256 x BN tile.  Each CTA
+// stages ITS 128 rows of A and HALF of the B tile (BN/2 rows); the leader CTA's single thread issues
+// tcgen05.mma.cta_group::2 (M = 256), which reads both CTAs' shared memory and writes each CTA's 128 accumulator
+// rows into that CTA's TMEM.  Per K block an SM therefore ingests 16 KB (A) + BN/2*128 B (B) for 128 x BN of MMA
+// work -- half the B traffic of the 1-CTA kernel, which is what bounds it (profiles/r01_gemm_pipeline_trace.txt).
+//   full_bar  (leader's only): 1 arrival (leader's arrive.expect_tx of both CTAs' bytes) + complete_tx of all loads;
+//             the peer's TMA loads signal the leader's barrier (cp.async.bulk.tensor.cta_group::2 + mapa address)
+//   empty_bar (one per CTA)  : the leader's tcgen05.commit.cta_group::2 multicast frees the slot in both CTAs
+//   tmem_full (one per CTA)  : same multicast commit after the last K block
+template <int BN, int STAGES>
+struct Gemm2Smem {
+  static constexpr int A_BYTES = 128 * 128;
+  static constexpr int B_BYTES = (BN / 2) * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;
+};
+
+template <bool A_MN, bool B_MN, int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+  using T = GemmTile<2>;
+  using SM = Gemm2Smem<BN, STAGES>;
+  static_assert(BN == 128 || BN == 256, "BN");
+  static_assert(4 * EpiStage<BN>::WARP_BYTES <= STAGES * SM::STAGE_BYTES, "staging does not fit in the pipeline smem");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();          // 0 = leader; the pair is adjacent along grid x (cluster 2x1x1):
+  const bool leader = crank == 0;                    // cta_group::2 pairs CTAs of consecutive cluster rank
+  const int m0 = blockIdx.x * T::BM;                 // this CTA's 128 rows (pair: blockIdx.x = 2p, 2p+1)
+  const int n0 = blockIdx.y * BN;
+
+  int kb_begin = blockIdx.z * g.kb_per_split;
+  int kb_end = min(kb_begin + g.kb_per_split, g.kb_total);
+  const int num_kb = kb_end - kb_begin;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      mbar_init(tmem_full_bar, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc_2sm(tmem_slot, BN);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      const int nb0 = n0 + (int)crank * (BN / 2);      // this CTA's half of the B tile
+      for (int base = 0; base < num_kb; base += STAGES) {
+        const uint32_t ph = (base / STAGES) & 1;
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+          if (base + s < num_kb) {
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * SM::STAGE_BYTES);   // bytes of both CTAs
+            const uint32_t bar = mapa_shared(&full_bar[s], 0);                       // the leader's barrier
+            uint8_t* a_dst = smem + s * SM::STAGE_BYTES;
+            uint8_t* b_dst = a_dst + SM::A_BYTES;
+            const int k0 = (kb_begin + base + s) * T::BK;
+            if constexpr (!A_MN) {
+              tma_load_2d_2sm(a_dst, &tmA, bar, k0, m0);
+            } else {
+#pragma unroll
+              for (int i = 0; i < T::BM / T::ATOM; ++i)
+                tma_load_2d_2sm(a_dst + i * (T::BK * 128), &tmA, bar, m0 + i * T::ATOM, k0);
+            }
+            if constexpr (!B_MN) {
+              tma_load_2d_2sm(b_dst, &tmB, bar, k0, nb0);
+            } else {
+#pragma unroll
+              for (int i = 0; i < (BN / 2) / T::ATOM; ++i)
+                tma_load_2d_2sm(b_dst + i * (T::BK * 128), &tmB, bar, nb0 + i * T::ATOM, k0);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader && lane == 0) {
+      const uint32_t sb16 = smem_u32(smem) >> 4;
+      const uint32_t dhi = smem_desc_hi_sw128(1024);
+      constexpr uint32_t A_LBO = A_MN ? T::BK * 128 : 0, B_LBO = B_MN ? T::BK * 128 : 0;
+      constexpr uint32_t A_KSTEP = A_MN ? T::UK * 128 : 32, B_KSTEP = B_MN ? T::UK * 128 : 32;
+      for (int base = 0; base < num_kb; base += STAGES) {
+        const uint32_t ph = (base / STAGES) & 1;
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+          if (base + s < num_kb) {
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < T::BK / T::UK; ++k) {
+              const uint64_t adesc = smem_desc_from(dhi, sb16 + ((s * SM::STAGE_BYTES + k * A_KSTEP) >> 4), A_LBO);
+              const uint64_t bdesc =
+                  smem_desc_from(dhi, sb16 + ((s * SM::STAGE_BYTES + SM::A_BYTES + k * B_KSTEP) >> 4), B_LBO);
+              tc_mma_f16_2sm(tmem_base, adesc, bdesc, g.idesc, (s | k) != 0 ? 1u : (uint32_t)(base != 0));
+            }
+            tc_commit_2sm(&empty_bar[s]);
+          }
+        }
+      }
+      tc_commit_2sm(tmem_full_bar);
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (both CTAs, warps 2..5)
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    gemm_epilogue_warp<BN>(g, tmem_base + ((uint32_t)(q * 32) << 16), m0 + q * 32, n0,
+                           smem + q * EpiStage<BN>::WARP_BYTES, lane, nullptr);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                      // both CTAs are done with TMEM and with each other's barriers
+  if (warp == 1) tmem_dealloc_2sm(tmem_base, BN);
 }
 
 #endif  // __CUDACC__

@@ -46,8 +46,9 @@ unsigned long long magb200_launch_count(void);
 int magb200_device_check(void);
 
 /* tuning/debug hook: trace_dev (device, 64 x uint64 per CTA, or NULL) receives clock64 stamps of the GEMM
- * pipeline; cfg selects the tile configuration (0 = default 128x128x3 stages, 1 = 4 stages, 2 = 6 stages,
- * 3 = 128x256x3, 4 = 128x256x4). */
+ * pipeline; cfg selects the tile configuration: 0 = default (128x128, 3 stages, 2-CTA clusters multicasting the A
+ * tile whenever the number of N tiles is even), 5 = the same without clusters, 1 = 128x128 4 stages,
+ * 3 = 128x256x3, 4 = 128x256x4 (no clusters). */
 void magb200_gemm_set_debug(void* trace_dev, int cfg);
 
 /* D[M,N] = A[M,K] * B[N,K]^T on tcgen05 tensor cores (TMA-fed, TMEM accumulators).

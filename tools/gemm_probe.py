@@ -18,6 +18,7 @@ DT = {"f16": (L.F16, torch.float16), "bf16": (L.BF16, torch.bfloat16), "tf32": (
 def run(name, M, N, K, adt, bdt, a_mn, b_mn, epi="f32", splits=1, bias=False, n_split=0, k_start_hi=0, alpha=1.0):
     lib = L.load()
     L.check(lib.magb200_device_check())
+    lib.magb200_gemm_set_debug(None, int(os.environ.get("MAGB200_GEMM_CFG", "0")))
     g = torch.Generator(device="cuda").manual_seed(1)
     A = torch.randn(M, K, device="cuda", generator=g).to(DT[adt][1])
     B = torch.randn(N, K, device="cuda", generator=g).to(DT[bdt][1])

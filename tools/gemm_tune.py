@@ -48,17 +48,17 @@ def bench(cfg, hot=False):
 for hot in (True,):
     print("== L2-hot (same buffers)" if hot else "== cold (rotating buffers > L2)")
     table = {}
-    for cfg in (0, 4):
+    for cfg in (0, 7, 8):
         try:
             table[cfg] = bench(cfg, hot)
         except Exception as e:
             print("cfg", cfg, "failed:", e); table[cfg] = None
     for i, s in enumerate(SHAPES):
         row = f"{s[0]:18s}"
-        for cfg in (0, 4):
+        for cfg in (0, 7, 8):
             row += "   n/a      " if table[cfg] is None else f"  {table[cfg][i][1]:6.1f}us {table[cfg][i][2]:5.0f}TF"
         print(row)
-print("cfg: 0=128x128x3st(2cta/sm) 1=128x128x4st 2=128x128x6st 3=128x256x3st 4=128x256x4st")
+print("columns: cfg 0 = 1-CTA 128x128 | cfg 7 = 2-CTA pair tiles 256x128 | cfg 8 = 2-CTA 256x256 where N >= 1024")
 
 # pipeline trace for attn_out shape, cfg 0 and cfg 2
 for cfg in (0,):
