@@ -45,15 +45,44 @@ __device__ __forceinline__ void load_tile(const __half* __restrict__ g, int ld, 
     *reinterpret_cast<uint4*>(s + r * PITCH + c) = v;
   }
 }
-// same, but stored transposed: s[c][r]
+// same, but stored transposed: s[c][r].  Consecutive lanes take consecutive source rows, so the 2-byte
+// transposed stores of a warp fall into consecutive halfs of one smem row (no bank conflicts).
 __device__ __forceinline__ void load_tile_t(const __half* __restrict__ g, int ld, int S, __half* s) {
   for (int i = threadIdx.x; i < SP * 8; i += blockDim.x) {
-    const int r = i >> 3, c = (i & 7) * 8;
+    const int r = i & (SP - 1), c = (i >> 6) * 8;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (r < S) v = *reinterpret_cast<const uint4*>(g + (int64_t)r * ld + c);
     const __half* h = reinterpret_cast<const __half*>(&v);
 #pragma unroll
     for (int k = 0; k < 8; ++k) s[(c + k) * PITCH + r] = h[k];
+  }
+}
+
+// Asynchronous variant (cp.async, 16 B per request, rows >= S zero-filled): all tiles of a CTA are requested
+// back to back and awaited once, instead of paying one global-load latency per tile (the ncu source view showed
+// ~40 % of the backward kernel's samples stalled on the first shared-memory store after each tile's loads).
+__device__ __forceinline__ void load_tile_async(const __half* __restrict__ g, int ld, int S, __half* s) {
+  for (int i = threadIdx.x; i < SP * 8; i += blockDim.x) {
+    const int r = i >> 3, c = (i & 7) * 8;
+    const bool ok = r < S;
+    const __half* src = g + (int64_t)(ok ? r : 0) * ld + c;
+    const uint32_t n = ok ? 16u : 0u;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(s + r * PITCH + c)), "l"(src), "r"(n)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void async_wait_all() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+// dst[c][r] = src[r][c] for a [64][64] tile already in shared memory (consecutive lanes -> consecutive r)
+__device__ __forceinline__ void transpose_tile(const __half* src, __half* dst) {
+  for (int i = threadIdx.x; i < SP * 8; i += blockDim.x) {
+    const int r = i & (SP - 1), c = (i >> 6) * 8;
+    const uint4 v = *reinterpret_cast<const uint4*>(src + r * PITCH + c);
+    const __half* h = reinterpret_cast<const __half*>(&v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dst[(c + k) * PITCH + r] = h[k];
   }
 }
 
@@ -81,6 +110,31 @@ __device__ __forceinline__ float drop_scale(uint64_t seed, uint32_t site, uint64
   return w >= thresh ? dscale : 0.f;
 }
 
+// Keep-flags of one (batch, head) probability tile, generated cooperatively: the S*S elements are a contiguous
+// index range [base, base + S*S), i.e. ~S*S/4 Philox counters for the whole CTA (the per-element form costs every
+// thread one full Philox-4x32-10 per probability it holds: 32 calls, more instructions than the five tile matmuls
+// together).  One bit per element, bit (q * S + key); a thread owns whole 32-bit words so no atomics are needed.
+__device__ __forceinline__ void fill_keep_bits(uint32_t* keep, uint64_t seed, uint32_t site, uint64_t base, int n,
+                                               uint32_t thresh) {
+  const int words = (n + 31) >> 5;
+  for (int wd = threadIdx.x; wd < words; wd += blockDim.x) {
+    const uint64_t first = base + 32ull * wd;
+    const uint64_t last = first + 31;
+    uint32_t bits = 0;
+    for (uint64_t c = first >> 2; c <= (last >> 2); ++c) {
+      const uint4 u = philox4x32(seed, site, c);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int64_t loc = (int64_t)(4 * c + k) - (int64_t)first;     // bit position inside this word
+        if (loc >= 0 && loc < 32 && w[k] >= thresh) bits |= 1u << loc;
+      }
+    }
+    keep[wd] = bits;
+  }
+}
+__device__ __forceinline__ bool keep_bit(const uint32_t* keep, int idx) { return (keep[idx >> 5] >> (idx & 31)) & 1u; }
+
 // the same for two consecutive elements idx, idx+1 (one Philox call when they share a counter)
 __device__ __forceinline__ void drop_scale2(uint64_t seed, uint32_t site, uint64_t idx, uint32_t thresh, float dscale,
                                             float& d0, float& d1) {
@@ -100,14 +154,20 @@ __global__ void __launch_bounds__(128) sdpa_fwd_mma_kernel(const __half* __restr
   const uint64_t seed = seed_in.ptr ? *seed_in.ptr : seed_in.value;
   __shared__ __align__(16) __half sQ[SP * PITCH];
   __shared__ __align__(16) __half sK[SP * PITCH];
+  __shared__ __align__(16) __half sV[SP * PITCH];
   __shared__ __align__(16) __half sVt[D * PITCH];
+  __shared__ uint32_t sKeep[SP * SP / 32];
   const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int Hd = heads * D, ld = 3 * Hd;
   const __half* base = qkv + (int64_t)b * S * ld + h * D;
-  load_tile(base, ld, S, sQ);
-  load_tile(base + Hd, ld, S, sK);
-  load_tile_t(base + 2 * Hd, ld, S, sVt);
+  load_tile_async(base, ld, S, sQ);
+  load_tile_async(base + Hd, ld, S, sK);
+  load_tile_async(base + 2 * Hd, ld, S, sV);
+  if (thresh != 0) fill_keep_bits(sKeep, seed, site, ((uint64_t)b * heads + h) * S * S, S * S, thresh);
+  async_wait_all();
+  __syncthreads();
+  transpose_tile(sV, sVt);
   __syncthreads();
   const int r0 = warp * 16;
   if (r0 >= S) return;
@@ -166,14 +226,15 @@ __global__ void __launch_bounds__(128) sdpa_fwd_mma_kernel(const __half* __restr
     if (i0 < S) lse[((int64_t)b * heads + h) * S + i0] = mx0 + logf(sum0);
     if (i1 < S) lse[((int64_t)b * heads + h) * S + i1] = mx1 + logf(sum1);
   }
-  const uint64_t bh = (uint64_t)b * heads + h;
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
     const int j = nt * 8 + 2 * t;
     float d00 = 1.f, d01 = 1.f, d10 = 1.f, d11 = 1.f;
     if (thresh != 0) {
-      drop_scale2(seed, site, (bh * S + i0) * S + j, thresh, dscale, d00, d01);
-      drop_scale2(seed, site, (bh * S + i1) * S + j, thresh, dscale, d10, d11);
+      d00 = keep_bit(sKeep, i0 * S + j) ? dscale : 0.f;
+      d01 = keep_bit(sKeep, i0 * S + j + 1) ? dscale : 0.f;
+      d10 = keep_bit(sKeep, i1 * S + j) ? dscale : 0.f;
+      d11 = keep_bit(sKeep, i1 * S + j + 1) ? dscale : 0.f;
     }
     sc[nt][0] *= inv0 * d00; sc[nt][1] *= inv0 * d01;
     sc[nt][2] *= inv1 * d10; sc[nt][3] *= inv1 * d11;
@@ -208,6 +269,7 @@ struct BwdSmem {
   float Dq[SP];        // rowsum(dO * O) per query
   float lse[SP];
   float bias[3 * D];   // column sums of dQ | dK | dV for this head
+  uint32_t keep[SP * SP / 32];   // dropout keep bits of the probability tile, bit (q * S + key)
 };
 
 // column sums (over the 16 rows of this warp's tile) of a C-layout accumulator -> smem accumulator[64]
@@ -242,31 +304,47 @@ __global__ void __launch_bounds__(128) sdpa_bwd_mma_kernel(const __half* __restr
   const int Hd = heads * D, ld = 3 * Hd;
   const __half* base = qkv + (int64_t)b * S * ld + h * D;
   const __half* dObase = dctx + (int64_t)b * S * Hd + h * D;
-  load_tile(base, ld, S, sm.q);
-  load_tile(base + Hd, ld, S, sm.k);
-  load_tile(base + 2 * Hd, ld, S, sm.v);
-  load_tile(dObase, Hd, S, sm.dO);
-  load_tile_t(base, ld, S, sm.qt);
-  load_tile_t(base + Hd, ld, S, sm.kt);
-  load_tile_t(dObase, Hd, S, sm.dOt);
+  load_tile_async(base, ld, S, sm.q);
+  load_tile_async(base + Hd, ld, S, sm.k);
+  load_tile_async(base + 2 * Hd, ld, S, sm.v);
+  load_tile_async(dObase, Hd, S, sm.dO);
   for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) sm.bias[i] = 0.f;
-  if (threadIdx.x < SP) {
-    const int i = threadIdx.x;
-    float acc = 0.f, l = 0.f;
+  if (thresh != 0) fill_keep_bits(sm.keep, seed, site, ((uint64_t)b * heads + h) * S * S, S * S, thresh);
+  {
+    // D[q] = sum_d dO[q][d] * O[q][d]: two threads per query (32 head dims each), 16-byte loads
+    const int i = threadIdx.x >> 1, half = threadIdx.x & 1;
+    float acc = 0.f;
     if (i < S) {
-      const __half* o = ctx + ((int64_t)b * S + i) * Hd + h * D;
-      const __half* d = dObase + (int64_t)i * Hd;
-#pragma unroll 8
-      for (int c = 0; c < D; c += 2) {
-        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(o + c));
-        const float2 e = __half22float2(*reinterpret_cast<const __half2*>(d + c));
-        acc += a.x * e.x + a.y * e.y;
+      const __half* o = ctx + ((int64_t)b * S + i) * Hd + h * D + half * 32;
+      const __half* d = dObase + (int64_t)i * Hd + half * 32;
+      uint4 ov[4], dv[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        ov[c] = *reinterpret_cast<const uint4*>(o + c * 8);
+        dv[c] = *reinterpret_cast<const uint4*>(d + c * 8);
       }
-      l = lse[((int64_t)b * heads + h) * S + i];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const __half2* oh = reinterpret_cast<const __half2*>(&ov[c]);
+        const __half2* dh = reinterpret_cast<const __half2*>(&dv[c]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 a = __half22float2(oh[k]), e = __half22float2(dh[k]);
+          acc += a.x * e.x + a.y * e.y;
+        }
+      }
     }
-    sm.Dq[i] = acc;
-    sm.lse[i] = l;
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (half == 0) {
+      sm.Dq[i] = acc;
+      sm.lse[i] = i < S ? lse[((int64_t)b * heads + h) * S + i] : 0.f;
+    }
   }
+  async_wait_all();
+  __syncthreads();
+  transpose_tile(sm.q, sm.qt);
+  transpose_tile(sm.k, sm.kt);
+  transpose_tile(sm.dO, sm.dOt);
   __syncthreads();
   const int64_t* mrow = mask ? mask + (int64_t)b * S : nullptr;
   const int r0 = warp * 16;
@@ -308,7 +386,7 @@ __global__ void __launch_bounds__(128) sdpa_bwd_mma_kernel(const __half* __restr
         float p = 0.f, dsv = 0.f, pdv = 0.f;
         if (key < S && qi < S) {
           p = expf(st[nt][e] * 0.125f + ((e < 2) ? m0 : m1) - sm.lse[qi]);
-          const float ds = drop_scale(seed, site, (bh * S + qi) * S + key, thresh, dscale);
+          const float ds = thresh == 0 ? 1.f : (keep_bit(sm.keep, qi * S + key) ? dscale : 0.f);
           pdv = p * ds;
           dsv = p * (dp[nt][e] * ds - sm.Dq[qi]) * 0.125f;      // includes d(score)/d(qk) = 1/sqrt(64)
         }

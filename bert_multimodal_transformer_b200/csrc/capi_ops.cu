@@ -173,6 +173,23 @@ int magb200_bert_backward_part(const magb200_bert_dims* dims, const int64_t* off
                             attention_mask, workspace, workspace_bytes, dlogits_scaled, grads, layer_hi, layer_lo, flags, ST);
 }
 
+int magb200_bert_backward_adamw(const magb200_bert_dims* dims, const int64_t* off, float* params, void* params16,
+                                const int64_t* input_ids, const int64_t* token_type_ids, const int64_t* attention_mask,
+                                void* workspace, size_t workspace_bytes, const float* dlogits_scaled, float* grads,
+                                float* exp_avg, float* exp_avg_sq, const uint8_t* decay_chunk, float lr, float beta1,
+                                float beta2, float eps, float weight_decay, int step, float grad_unscale, int zero_grad,
+                                const float* hyper_dev, void* stream) {
+  OptHook h;
+  h.params = params; h.params16 = reinterpret_cast<__half*>(params16); h.exp_avg = exp_avg; h.exp_avg_sq = exp_avg_sq;
+  h.decay_chunk = decay_chunk; h.lr = lr; h.beta1 = beta1; h.beta2 = beta2; h.eps = eps; h.weight_decay = weight_decay;
+  h.step = step; h.grad_unscale = grad_unscale; h.zero_grad = zero_grad; h.hyper_dev = hyper_dev;
+  MAGB_REQUIRE(params != nullptr && grads != nullptr && exp_avg != nullptr && exp_avg_sq != nullptr &&
+                   decay_chunk != nullptr, "magb200_bert_backward_adamw: null optimizer buffer");
+  return bert_backward_part(*dims, off, params, reinterpret_cast<const __half*>(params16), input_ids, token_type_ids,
+                            attention_mask, workspace, workspace_bytes, dlogits_scaled, grads, dims->layers - 1, 0, 3, ST,
+                            &h);
+}
+
 int magb200_bert_peek(const magb200_bert_dims* dims, void* workspace, int what, int layer, void* out, size_t out_bytes,
                       void* stream) {
   return bert_peek(*dims, workspace, what, layer, out, out_bytes, ST);

@@ -51,6 +51,7 @@ struct EmbedArgs {
   float eps = 1e-12f;
   float p = 0.f; Seed seed; uint32_t site = 0;
   int V = 0, A = 0, KA = 896, T = 0, S = 0, vocab = 0, hidden = 768;
+  int type_vocab = 2;                // rows of the token-type table (backward: type >= type_vocab is clamped)
   float* emb32 = nullptr;            // [T][768]
   __half* amag = nullptr;            // [T][KA] or null
 };
@@ -141,9 +142,18 @@ int bert_forward(const magb200_bert_dims& d, const int64_t* off, const float* P,
 int bert_backward(const magb200_bert_dims& d, const int64_t* off, const float* P, const __half* P16, const int64_t* ids,
                   const int64_t* tt, const int64_t* mask, void* workspace, size_t ws_bytes, const float* dlogits_scaled,
                   float* G, cudaStream_t st);
+// AdamW fused into the backward schedule (model_bert.cu): slices of the flat buffers are updated while the
+// backward pass of the layers below is still running.  Field meaning as magb200_adamw_step.
+struct OptHook {
+  float* params = nullptr; __half* params16 = nullptr; float* exp_avg = nullptr; float* exp_avg_sq = nullptr;
+  const uint8_t* decay_chunk = nullptr;
+  float lr = 0.f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-6f, weight_decay = 0.f;
+  int step = 1; float grad_unscale = 1.f; int zero_grad = 1; const float* hyper_dev = nullptr;
+};
 int bert_backward_part(const magb200_bert_dims& d, const int64_t* off, const float* P, const __half* P16,
                        const int64_t* ids, const int64_t* tt, const int64_t* mask, void* workspace, size_t ws_bytes,
-                       const float* dlogits_scaled, float* G, int layer_hi, int layer_lo, int flags, cudaStream_t st);
+                       const float* dlogits_scaled, float* G, int layer_hi, int layer_lo, int flags, cudaStream_t st,
+                       const OptHook* opt = nullptr);
 int bert_peek(const magb200_bert_dims& d, void* workspace, int what, int layer, void* out, size_t out_bytes,
               cudaStream_t st);
 }  // namespace magb200

@@ -8,6 +8,7 @@
 // buffer that mirrors the parameter buffer.  Activation gradients inside backward carry
 // dims.grad_scale (loss scaling: the backward GEMM operands are fp16); every parameter-gradient
 // write multiplies by 1/grad_scale.
+#include <stdlib.h>
 #include "common.cuh"
 #include "gemm_sm100.cuh"
 #include "host.h"
@@ -42,7 +43,10 @@ struct BertWs {
   LayerWs layer[MAGB200_MAX_LAYERS];
   float* pre32; float* poolpre32; float* pooled32;
   // backward scratch
-  float* dy32; float* dr32; __half* dpre16; __half* du16; __half* dctx16; __half* dqkv16; __half* dG16;
+  // The fp16 gradient tensors the weight-gradient GEMMs consume exist twice (layer parity): those GEMMs run on a
+  // side stream and may still be reading layer l+1's copy while the main chain produces layer l's.
+  float* dy32; float* dr32; __half* dpre_f16[2]; __half* dpre_a16[2]; __half* du16[2]; __half* dctx16;
+  __half* dqkv16[2]; __half* dG16;
   float* dBmag32; __half* dpool16;
   size_t bytes;
 };
@@ -75,10 +79,13 @@ BertWs carve_ws(const magb200_bert_dims& d, void* base) {
   w.pooled32 = c.take<float>((size_t)d.batch * H);
   w.dy32 = c.take<float>(T * H);
   w.dr32 = c.take<float>(T * H);
-  w.dpre16 = c.take<__half>(T * H);
-  w.du16 = c.take<__half>(T * I);
+  for (int k = 0; k < 2; ++k) {
+    w.dpre_f16[k] = c.take<__half>(T * H);
+    w.dpre_a16[k] = c.take<__half>(T * H);
+    w.du16[k] = c.take<__half>(T * I);
+    w.dqkv16[k] = c.take<__half>(T * 3 * H);
+  }
   w.dctx16 = c.take<__half>(T * H);
-  w.dqkv16 = c.take<__half>(T * 3 * H);
   w.dG16 = c.take<__half>(T * 4 * H);
   w.dBmag32 = c.take<float>((size_t)4 * H * d.ka);
   w.dpool16 = c.take<__half>((size_t)d.batch * H);
@@ -103,6 +110,30 @@ enum : uint32_t { SITE_EMB = 1, SITE_MAG = 2, SITE_CLS = 3, SITE_LAYER0 = 16 };
 inline uint32_t site_attn_prob(int l) { return SITE_LAYER0 + 4 * l; }
 inline uint32_t site_attn_out(int l) { return SITE_LAYER0 + 4 * l + 1; }
 inline uint32_t site_ffn_out(int l) { return SITE_LAYER0 + 4 * l + 2; }
+
+// Side stream for the weight-gradient GEMMs and bias column sums of the encoder layers.  They depend only on the
+// activation-gradient tensor just produced and on saved activations, nothing downstream reads their results before
+// the optimizer (or the gradient all-reduce of the piece), so they fill the SMs the main dgrad chain leaves idle in
+// its partial last waves.  Ordering uses events only (valid eagerly and under stream capture, where the side stream
+// joins the capture through the first wait and is joined back before the piece returns).
+constexpr int MAGB200_MAX_DEVICES = 16;
+struct SideCtx {
+  cudaStream_t stream = nullptr, opt = nullptr;
+  cudaEvent_t fork = nullptr, done[2] = {nullptr, nullptr}, join = nullptr, lay = nullptr, optjoin = nullptr;
+  bool enabled = true;
+  bool init() {
+    if (stream) return true;
+    const char* e = getenv("MAGB200_SIDE_STREAM");
+    if (e && e[0] == '0') { enabled = false; return true; }
+    if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) return false;
+    if (cudaStreamCreateWithFlags(&opt, cudaStreamNonBlocking) != cudaSuccess) return false;
+    cudaEvent_t* evs[6] = {&fork, &done[0], &done[1], &join, &lay, &optjoin};
+    for (cudaEvent_t* ev : evs)
+      if (cudaEventCreateWithFlags(ev, cudaEventDisableTiming) != cudaSuccess) return false;
+    return true;
+  }
+};
+SideCtx g_side[MAGB200_MAX_DEVICES];
 
 #define RUN(expr)            \
   do {                       \
@@ -203,7 +234,8 @@ int bert_forward(const magb200_bert_dims& d, const int64_t* off, const float* P,
 int bert_backward(const magb200_bert_dims& d, const int64_t* off, const float* P, const __half* P16,
                   const int64_t* ids, const int64_t* tt, const int64_t* mask, void* workspace, size_t ws_bytes,
                   const float* dlogits_scaled, float* G, cudaStream_t st) {
-  return bert_backward_part(d, off, P, P16, ids, tt, mask, workspace, ws_bytes, dlogits_scaled, G, d.layers - 1, 0, 3, st);
+  return bert_backward_part(d, off, P, P16, ids, tt, mask, workspace, ws_bytes, dlogits_scaled, G, d.layers - 1, 0, 3, st,
+                            nullptr);
 }
 
 // Backward in pieces so the caller can all-reduce finished gradient ranges while later pieces run:
@@ -211,7 +243,8 @@ int bert_backward(const magb200_bert_dims& d, const int64_t* off, const float* P
 // bit 1 = run the tail (MAG + embeddings) afterwards.  The running activation gradient lives in the workspace.
 int bert_backward_part(const magb200_bert_dims& d, const int64_t* off, const float* P, const __half* P16,
                        const int64_t* ids, const int64_t* tt, const int64_t* mask, void* workspace, size_t ws_bytes,
-                       const float* dlogits_scaled, float* G, int layer_hi, int layer_lo, int flags, cudaStream_t st) {
+                       const float* dlogits_scaled, float* G, int layer_hi, int layer_lo, int flags, cudaStream_t st,
+                       const OptHook* opt) {
   RUN(check_dims(d));
   MAGB_REQUIRE(layer_hi < d.layers && layer_lo >= 0, "bert_backward_part: layer range [%d, %d] out of bounds", layer_lo, layer_hi);
   MAGB_REQUIRE(d.seq <= 128, "bert_backward: seq=%d > 128 not supported by the attention backward yet", d.seq);
@@ -220,6 +253,46 @@ int bert_backward_part(const magb200_bert_dims& d, const int64_t* off, const flo
   const int B = d.batch, S = d.seq, T = B * S, H = d.hidden, I = d.inter;
   const float us = 1.0f / d.grad_scale;   // parameter gradients are stored unscaled
   const Seed sd{d.seed, d.seed_dev};
+  int dev = 0;
+  MAGB_CHECK_CUDA(cudaGetDevice(&dev));
+  MAGB_REQUIRE(dev >= 0 && dev < MAGB200_MAX_DEVICES, "bert_backward: device index %d out of range", dev);
+  SideCtx& sc = g_side[dev];
+  MAGB_REQUIRE(sc.init(), "bert_backward: cannot create the side stream / events");
+  const bool side = sc.enabled;
+  cudaStream_t sst = side ? sc.stream : st;
+  // main -> side: everything enqueued on `st` so far is visible to what the side stream runs next
+  auto fork = [&]() -> int {
+    if (!side) return 0;
+    MAGB_CHECK_CUDA(cudaEventRecord(sc.fork, st));
+    MAGB_CHECK_CUDA(cudaStreamWaitEvent(sst, sc.fork, 0));
+    return 0;
+  };
+  bool side_used = false, opt_used = false;
+  int layers_done = 0;
+  // Optimizer hook (single-process training): AdamW over a layer's slice of the flat buffers is enqueued on a third
+  // stream as soon as that layer's weight gradients (side stream) are complete and the main chain has left the
+  // layer (its dgrad GEMMs read the fp16 weights AdamW rewrites).  AdamW is HBM-bound, the GEMM chain is not, so
+  // the update of layers L-1 .. 1 disappears behind the backward pass of the layers below.
+  cudaStream_t ost = (opt && side) ? sc.opt : st;
+  auto adamw_range = [&](int64_t s0, int64_t s1, cudaStream_t stream) -> int {
+    if (s1 <= s0) return 0;
+    MAGB_REQUIRE(s0 % 256 == 0 && s1 % 256 == 0, "backward_adamw: slice [%lld, %lld) is not 256-aligned", (long long)s0,
+                 (long long)s1);
+    return adamw_step(opt->params + s0, G + s0, opt->exp_avg + s0, opt->exp_avg_sq + s0,
+                      opt->params16 ? opt->params16 + s0 : nullptr, opt->decay_chunk + s0 / 256, s1 - s0, opt->lr,
+                      opt->beta1, opt->beta2, opt->eps, opt->weight_decay, opt->step, opt->grad_unscale, opt->zero_grad,
+                      opt->hyper_dev, stream);
+  };
+  auto layer_start = [&](int l) -> int64_t {
+    return l < d.layers ? off[MAGB200_OFF_LAYER0 + (int64_t)l * MAGB200_OFF_PER_LAYER + MAGB200_LOFF_QKV_W]
+                        : off[MAGB200_OFF_POOL_W];
+  };
+  if (opt) {
+    for (int l = 0; l < d.layers; ++l)
+      MAGB_REQUIRE(layer_start(l) < layer_start(l + 1) && layer_start(0) > off[MAGB200_OFF_EMB_LN_B],
+                   "backward_adamw: flat order must be [embeddings | layers ascending | pooler, MAG, classifier]");
+    MAGB_REQUIRE(off[MAGB200_OFF_TOTAL] > off[MAGB200_OFF_POOL_W], "backward_adamw: bad OFF_TOTAL");
+  }
 
   if (flags & 1) {
   // classifier + pooler                                                         bert.py:304-307, 231
@@ -234,30 +307,66 @@ int bert_backward_part(const magb200_bert_dims& d, const int64_t* off, const flo
   for (int l = layer_hi; l >= layer_lo; --l) {
     const int64_t* o = off + MAGB200_OFF_LAYER0 + (int64_t)l * MAGB200_OFF_PER_LAYER;
     LayerWs& L = w.layer[l];
+    const int par = l & 1;
+    __half* dpre_f = w.dpre_f16[par];
+    __half* dpre_a = w.dpre_a16[par];
+    __half* du = w.du16[par];
+    __half* dqkv = w.dqkv16[par];
+    // this layer overwrites the gradient copies the side stream read two layers ago
+    if (side && layers_done >= 2) MAGB_CHECK_CUDA(cudaStreamWaitEvent(st, sc.done[par], 0));
     // BertOutput: LayerNorm(dropout(dense(g)) + a)
     RUN(ln_bwd(w.dy32, w.x32[l + 1], P + o[MAGB200_LOFF_LN2_W], P + o[MAGB200_LOFF_LN2_B], L.rstd2, d.p_hidden, sd,
-               site_ffn_out(l), T, us, w.dr32, w.dpre16, G + o[MAGB200_LOFF_LN2_W], G + o[MAGB200_LOFF_LN2_B],
+               site_ffn_out(l), T, us, w.dr32, dpre_f, G + o[MAGB200_LOFF_LN2_W], G + o[MAGB200_LOFF_LN2_B],
                G + o[MAGB200_LOFF_F2_B], st));
-    RUN(linear_wgrad(w.dpre16, H, L.g16, I, T, H, I, G + o[MAGB200_LOFF_F2_W], I, 1, us, st));
-    RUN(linear_dgrad(w.dpre16, H, P16 + o[MAGB200_LOFF_F2_W], I, T, I, H, EPI_DGELU_F16, w.du16, L.u16, I, st));
+    RUN(fork());
+    RUN(linear_wgrad(dpre_f, H, L.g16, I, T, H, I, G + o[MAGB200_LOFF_F2_W], I, 1, us, sst));
+    RUN(linear_dgrad(dpre_f, H, P16 + o[MAGB200_LOFF_F2_W], I, T, I, H, EPI_DGELU_F16, du, L.u16, I, st));
     // BertIntermediate: gelu(dense(a))
-    RUN(colsum_f16(w.du16, T, I, us, G + o[MAGB200_LOFF_F1_B], st));
-    RUN(linear_wgrad(w.du16, I, L.a16, H, T, I, H, G + o[MAGB200_LOFF_F1_W], H, 1, us, st));
-    RUN(linear_dgrad(w.du16, I, P16 + o[MAGB200_LOFF_F1_W], H, T, H, I, EPI_STORE_F32, w.dr32, w.dr32, H, st));
+    RUN(fork());
+    RUN(colsum_f16(du, T, I, us, G + o[MAGB200_LOFF_F1_B], sst));
+    RUN(linear_wgrad(du, I, L.a16, H, T, I, H, G + o[MAGB200_LOFF_F1_W], H, 1, us, sst));
+    RUN(linear_dgrad(du, I, P16 + o[MAGB200_LOFF_F1_W], H, T, H, I, EPI_STORE_F32, w.dr32, w.dr32, H, st));
     // BertSelfOutput: LayerNorm(dropout(dense(ctx)) + x)
     RUN(ln_bwd(w.dr32, L.a32, P + o[MAGB200_LOFF_LN1_W], P + o[MAGB200_LOFF_LN1_B], L.rstd1, d.p_hidden, sd,
-               site_attn_out(l), T, us, w.dy32, w.dpre16, G + o[MAGB200_LOFF_LN1_W], G + o[MAGB200_LOFF_LN1_B],
+               site_attn_out(l), T, us, w.dy32, dpre_a, G + o[MAGB200_LOFF_LN1_W], G + o[MAGB200_LOFF_LN1_B],
                G + o[MAGB200_LOFF_AO_B], st));
-    RUN(linear_wgrad(w.dpre16, H, L.ctx16, H, T, H, H, G + o[MAGB200_LOFF_AO_W], H, 4, us, st));
-    RUN(linear_dgrad(w.dpre16, H, P16 + o[MAGB200_LOFF_AO_W], H, T, H, H, EPI_STORE_F16, w.dctx16, nullptr, H, st));
+    RUN(fork());
+    RUN(linear_wgrad(dpre_a, H, L.ctx16, H, T, H, H, G + o[MAGB200_LOFF_AO_W], H, 4, us, sst));
+    RUN(linear_dgrad(dpre_a, H, P16 + o[MAGB200_LOFF_AO_W], H, T, H, H, EPI_STORE_F16, w.dctx16, nullptr, H, st));
     // BertSelfAttention
     RUN(sdpa_bwd(L.qkv16, w.dctx16, L.ctx16, L.lse, mask, B, S, d.heads, H / d.heads, d.p_attn, sd, site_attn_prob(l), us,
-                 w.dqkv16, G + o[MAGB200_LOFF_QKV_B], st));
-    RUN(linear_wgrad(w.dqkv16, 3 * H, w.x16[l], H, T, 3 * H, H, G + o[MAGB200_LOFF_QKV_W], H, 2, us, st));
-    RUN(linear_dgrad(w.dqkv16, 3 * H, P16 + o[MAGB200_LOFF_QKV_W], H, T, H, 3 * H, EPI_STORE_F32, w.dy32, w.dy32, H, st));
+                 dqkv, G + o[MAGB200_LOFF_QKV_B], st));
+    RUN(fork());
+    RUN(linear_wgrad(dqkv, 3 * H, w.x16[l], H, T, 3 * H, H, G + o[MAGB200_LOFF_QKV_W], H, 2, us, sst));
+    RUN(linear_dgrad(dqkv, 3 * H, P16 + o[MAGB200_LOFF_QKV_W], H, T, H, 3 * H, EPI_STORE_F32, w.dy32, w.dy32, H, st));
+    if (side) {
+      MAGB_CHECK_CUDA(cudaEventRecord(sc.done[par], sst));
+      side_used = true;
+    }
+    ++layers_done;
+    if (opt) {
+      if (side) {
+        MAGB_CHECK_CUDA(cudaEventRecord(sc.lay, st));
+        MAGB_CHECK_CUDA(cudaStreamWaitEvent(ost, sc.lay, 0));
+        MAGB_CHECK_CUDA(cudaStreamWaitEvent(ost, sc.done[par], 0));
+        opt_used = true;
+      }
+      RUN(adamw_range(layer_start(l), layer_start(l + 1), ost));
+    }
+  }
+  // join: the caller may all-reduce / consume this piece's gradients as soon as `st` gets here
+  if (side && side_used) {
+    MAGB_CHECK_CUDA(cudaEventRecord(sc.join, sst));
+    MAGB_CHECK_CUDA(cudaStreamWaitEvent(st, sc.join, 0));
   }
 
-  if (!(flags & 2)) return 0;
+  if (!(flags & 2)) {
+    if (opt && opt_used) {
+      MAGB_CHECK_CUDA(cudaEventRecord(sc.optjoin, ost));
+      MAGB_CHECK_CUDA(cudaStreamWaitEvent(st, sc.optjoin, 0));
+    }
+    return 0;
+  }
   // MAG (modeling.py:25-51)
   RUN(mag_tail_bwd(w.dy32, w.G32, w.emb32, P + off[MAGB200_OFF_MAG_LN_W], d.beta_shift, d.mag_ln_eps, d.p_mag, sd,
                    SITE_MAG, T, us, w.dG16, w.dr32, G + off[MAGB200_OFF_MAG_LN_W], G + off[MAGB200_OFF_MAG_LN_B],
@@ -275,8 +384,18 @@ int bert_backward_part(const magb200_bert_dims& d, const int64_t* off, const flo
   e.word = P + off[MAGB200_OFF_WORD]; e.pos = P + off[MAGB200_OFF_POS]; e.type = P + off[MAGB200_OFF_TYPE];
   e.gamma = P + off[MAGB200_OFF_EMB_LN_W]; e.beta = P + off[MAGB200_OFF_EMB_LN_B];
   e.eps = d.ln_eps; e.p = d.p_hidden; e.seed = sd; e.site = SITE_EMB; e.T = T; e.S = S; e.vocab = d.vocab;
+  e.type_vocab = d.type_vocab;
   RUN(embed_ln_bwd(e, w.dr32, us, G + off[MAGB200_OFF_WORD], G + off[MAGB200_OFF_POS], G + off[MAGB200_OFF_TYPE],
                    G + off[MAGB200_OFF_EMB_LN_W], G + off[MAGB200_OFF_EMB_LN_B], st));
+  if (opt) {
+    // what no layer slice covers: the embedding tables in front, pooler / MAG / classifier behind
+    RUN(adamw_range(0, layer_start(0), st));
+    RUN(adamw_range(off[MAGB200_OFF_POOL_W], off[MAGB200_OFF_TOTAL], st));
+    if (opt_used) {
+      MAGB_CHECK_CUDA(cudaEventRecord(sc.optjoin, ost));
+      MAGB_CHECK_CUDA(cudaStreamWaitEvent(st, sc.optjoin, 0));
+    }
+  }
   return 0;
 }
 

@@ -145,6 +145,16 @@ class BertEngine:
                                                     L.ptr(ws), ws.numel(), L.ptr(dlogits_scaled), L.ptr(grads), layer_hi,
                                                     layer_lo, flags, L.current_stream()))
 
+    def backward_adamw(self, dims, ws, input_ids, token_type_ids, attention_mask, dlogits_scaled, grads, exp_avg,
+                       exp_avg_sq, decay_chunks, lr, betas, eps, weight_decay, step, grad_unscale, hyper_dev):
+        """Backward and the AdamW update as one schedule (magb200_bert_backward_adamw): same result as backward()
+        followed by magb200_adamw_step over the flat buffer, with the per-layer updates overlapped."""
+        L.check(L.load().magb200_bert_backward_adamw(
+            byref(dims), self.offsets, L.ptr(self.flat), L.ptr(self.flat16), L.ptr(input_ids), L.ptr(token_type_ids),
+            L.ptr(attention_mask), L.ptr(ws), ws.numel(), L.ptr(dlogits_scaled), L.ptr(grads), L.ptr(exp_avg),
+            L.ptr(exp_avg_sq), L.ptr(decay_chunks), lr, betas[0], betas[1], eps, weight_decay, step, grad_unscale, 1,
+            L.ptr(hyper_dev) if hyper_dev is not None else None, L.current_stream()))
+
     def layer_grad_range(self, lo, hi):
         """[start, end) element range of the flat buffers covering encoder layers lo .. hi-1 (contiguous)."""
         start = self.offsets[L.OFF_LAYER0 + L.OFF_PER_LAYER * lo + L.LOFF_QKV_W]

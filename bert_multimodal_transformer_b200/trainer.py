@@ -15,6 +15,7 @@ its own slice of the batch; the only collective is the gradient all-reduce over 
 from __future__ import annotations
 
 import math
+import os
 from ctypes import byref, c_void_p
 
 import numpy as np
@@ -99,6 +100,7 @@ class MagBertTrainer:
         self.stream = torch.cuda.Stream(device=dev)
         self.comm_stream = torch.cuda.Stream(device=dev)
         self.overlap = overlap_allreduce
+        self.fused_optimizer = os.environ.get("MAGB200_FUSED_OPTIMIZER", "0") == "1"   # measured: no gain (L2-bound GEMMs and the HBM-bound update slow each other), see DESIGN.md
         eng.refresh_operands()
         self.kernel_launches_per_train_step = None
 
@@ -121,6 +123,15 @@ class MagBertTrainer:
                     i["acoustic"], self.logits)
         L.check(lib.magb200_mse_loss(L.ptr(self.logits), L.ptr(i["labels"]), self.B * eng.num_labels, eng.grad_scale,
                                      L.ptr(self.loss), L.ptr(self.dlogits), st))
+        if self.world == 1 and self.fused_optimizer and hasattr(eng, "backward_adamw"):
+            # backward + AdamW as one schedule: per-layer updates overlap the backward of the layers below
+            eng.backward_adamw(self.train_dims, self.ws, i["input_ids"], i["token_type_ids"], i["attention_mask"],
+                               self.dlogits, self.grads, self.exp_avg, self.exp_avg_sq, self.decay, self.lr, self.betas,
+                               self.eps, self.wd, 1, grad_unscale(self.world), self.dev_hyper)
+            eng.after_optimizer_step()
+            if transfers:
+                self.host_loss[slot].copy_(self.loss, non_blocking=True)
+            return
         if self.world > 1 and self.overlap and hasattr(eng, "backward_part"):
             self._backward_overlapped(i)
         else:

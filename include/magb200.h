@@ -213,6 +213,18 @@ int magb200_bert_backward_part(const magb200_bert_dims* dims, const int64_t* off
                                const int64_t* attention_mask, void* workspace, size_t workspace_bytes,
                                const float* dlogits_scaled, float* grads, int layer_hi, int layer_lo, int flags,
                                void* stream);
+/* Backward + optimizer of one training step as ONE schedule (multimodal_driver.py:378 + :383 for
+ * gradient_accumulation_step == 1, single process): identical results to magb200_bert_backward followed by
+ * magb200_adamw_step over the whole flat buffer, but the AdamW update of each encoder layer's slice is enqueued on an
+ * internal stream as soon as that layer's gradients are final, overlapping the HBM-bound update with the GEMM-bound
+ * backward of the layers below.  All work is ordered after what `stream` held at the call and joined back into
+ * `stream` before returning (legal under stream capture).  Optimizer arguments as magb200_adamw_step. */
+int magb200_bert_backward_adamw(const magb200_bert_dims* dims, const int64_t* off, float* params, void* params16,
+                                const int64_t* input_ids, const int64_t* token_type_ids, const int64_t* attention_mask,
+                                void* workspace, size_t workspace_bytes, const float* dlogits_scaled, float* grads,
+                                float* exp_avg, float* exp_avg_sq, const uint8_t* decay_chunk, float lr, float beta1,
+                                float beta2, float eps, float weight_decay, int step, float grad_unscale, int zero_grad,
+                                const float* hyper_dev, void* stream);
 /* copy a saved activation out of the workspace (tests): MAGB200_PEEK_* */
 int magb200_bert_peek(const magb200_bert_dims* dims, void* workspace, int what, int layer, void* out, size_t out_bytes,
                       void* stream);

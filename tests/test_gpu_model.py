@@ -204,3 +204,31 @@ def test_trainer_graph_step_equals_eager_step_and_learns():
     # same seeds, same kernels: graph replay and eager launches agree (up to fp32 atomic ordering)
     assert abs(start[False] - start[True]) < 1e-6
     assert abs(losses[False][0] - losses[True][0]) < 1e-4 and abs(losses[False][1] - losses[True][1]) < 1e-3
+
+
+def test_fused_backward_adamw_equals_backward_then_adamw():
+    """magb200_bert_backward_adamw (per-layer AdamW slices overlapped with the backward pass, weight-gradient GEMMs
+    on a side stream) must leave the same parameters and moments as backward followed by one AdamW launch."""
+    from bert_multimodal_transformer_b200.trainer import MagBertTrainer
+    b = gen.bert_batch(8, 50, seed=33)
+    args = (b["input_ids"], b["visual"], b["acoustic"], b["attention_mask"], b["token_type_ids"])
+    state = {}
+    for fused in (False, True):
+        for graph in (False, True):
+            model, _ = make_model(3, seed=9)
+            model.train()
+            tr = MagBertTrainer(model, 8, 50, lr=1e-3, total_steps=0, use_cuda_graph=graph, seed=11)
+            tr.fused_optimizer = fused
+            losses = [tr.train_step(*args, b["labels"]) for _ in range(2)]
+            torch.cuda.synchronize()
+            state[(fused, graph)] = (tr.eng.flat.clone(), tr.exp_avg.clone(), tr.exp_avg_sq.clone(), losses,
+                                     tr.grads.abs().max().item())
+    ref = state[(False, False)]
+    for key, cur in state.items():
+        assert cur[4] == 0.0, key                                       # gradients are zeroed by every variant
+        assert abs(cur[3][0] - ref[3][0]) < 1e-5, (key, cur[3], ref[3])
+        # one step of Adam moves every weight by ~lr regardless of the gradient's size, so compare the first moment
+        # (linear in the gradients of both steps) tightly and the weights loosely
+        scale = ref[1].abs().max().item()
+        assert (cur[1] - ref[1]).abs().max().item() < 5e-3 * scale, key
+        assert (cur[0] - ref[0]).abs().max().item() < 2.5e-3, key
