@@ -268,11 +268,44 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ---------------------------------------------------------------------------- math
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// erf-GELU (transformers 3.0.2 ACT2FN["gelu"] = F.gelu) without erff():  gelu(x) = x Phi(x),
+//   q(x) = 0.5 erfc(|x|/sqrt2) = 0.5 (a1 t + ... + a5 t^5) exp(-x^2/2),  t = 1/(1 + p |x|/sqrt2)
+// (Abramowitz-Stegun 7.1.26, |erf error| <= 1.5e-7; measured |gelu error| 3.3e-7 in fp32, the same as the erff form),
+//   Phi(x) = x >= 0 ? 1 - q : q,  gelu(x) = max(x, 0) - |x| q,  gelu'(x) = Phi(x) + x exp(-x^2/2) / sqrt(2 pi).
+// One MUFU.RCP + one MUFU.EX2 + ~10 FMA-pipe instructions; erff() costs ~24 and the GEMM epilogues that apply it to
+// every FFN activation are issue-bound (profiles/r01_gemm_persistent_trace.txt).
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// q(x) as above; e = exp(-x^2/2)
+__device__ __forceinline__ float gelu_tail(float x, float& e) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  poly = fmaf(t, poly, 0.5f * 1.421413741f);
+  poly = fmaf(t, poly, 0.5f * -0.284496736f);
+  poly = fmaf(t, poly, 0.5f * 0.254829592f);
+  poly *= t;
+  e = ex2_approx(z * z * -1.4426950408889634f);
+  return poly * e;
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  float e;
+  const float q = gelu_tail(x, e);
+  return fmaf(-fabsf(x), q, fmaxf(x, 0.f));
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float e;
+  const float q = gelu_tail(x, e);
+  const float cdf = x >= 0.f ? 1.0f - q : q;
+  return fmaf(x * 0.39894228040143268f, e, cdf);
 }
 
 // ---------------------------------------------------------------------------- dropout RNG

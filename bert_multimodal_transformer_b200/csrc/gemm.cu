@@ -157,7 +157,49 @@ static int launch2_majors(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUt
   return launch2_variant<true, true, BN, STAGES>(ta, tb, g, grid, st);
 }
 
-static int gemm_launch_2cta(const GemmProblem& p, int BN, cudaStream_t st) {
+// Persistent 2-CTA kernel: as many clusters as fit on the device at once (queried per variant), never more than tiles.
+template <bool A_MN, bool B_MN, int BN, int STAGES, int NEPI>
+static int launch2p_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, cudaStream_t st) {
+  using SM = Gemm2pSmem<BN, STAGES, NEPI>;
+  auto kern = gemm2p_tcgen05_kernel<A_MN, B_MN, BN, STAGES, NEPI>;
+  static int max_clusters[16] = {0};
+  int dev = 0;
+  MAGB_CHECK_CUDA(cudaGetDevice(&dev));
+  MAGB_REQUIRE(dev >= 0 && dev < 16, "gemm: device index %d out of range", dev);
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(64 + 32 * NEPI); cfg.dynamicSmemBytes = SM::TOTAL; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (max_clusters[dev] == 0) {
+    MAGB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    cudaDeviceProp prop;
+    MAGB_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev));
+    cfg.gridDim = dim3(2 * (prop.multiProcessorCount / 2), 1, 1);
+    int n = 0;
+    MAGB_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    MAGB_REQUIRE(n >= 1, "gemm: the persistent 2-CTA kernel does not fit on this device");
+    max_clusters[dev] = n < prop.multiProcessorCount / 2 ? n : prop.multiProcessorCount / 2;
+  }
+  const int total = g.tiles_m * g.tiles_n * g.splits;
+  const int ncl = total < max_clusters[dev] ? total : max_clusters[dev];
+  cfg.gridDim = dim3(2 * ncl, 1, 1);
+  MAGB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, g));
+  MAGB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+template <int BN, int STAGES, int NEPI>
+static int launch2p_majors(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g,
+                           cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch2p_variant<false, false, BN, STAGES, NEPI>(ta, tb, g, st);
+  if (!a_mn && b_mn) return launch2p_variant<false, true, BN, STAGES, NEPI>(ta, tb, g, st);
+  if (a_mn && !b_mn) return launch2p_variant<true, false, BN, STAGES, NEPI>(ta, tb, g, st);
+  return launch2p_variant<true, true, BN, STAGES, NEPI>(ta, tb, g, st);
+}
+
+static int gemm_launch_2cta(const GemmProblem& p, int BN, cudaStream_t st, bool persistent = false) {
   const int BK = 64, ATOM = 64, BM = 128;
   CUtensorMap ta, tb;
   int rc;
@@ -179,8 +221,8 @@ static int gemm_launch_2cta(const GemmProblem& p, int BN, cudaStream_t st) {
   g.epi = p.epi; g.bias = p.bias; g.out0 = p.out0; g.out1 = p.out1; g.aux = p.aux; g.ldo = p.ldo; g.alpha = p.alpha;
   const uint32_t fmt = p.a_dtype == DT_BF16 ? 1u : 0u;
   g.idesc = make_idesc(fmt, fmt, p.a_mn, p.b_mn, 256, BN);     // the pair's UMMA: M = 256
-  g.trace = nullptr;
-  g.dbg = 0;
+  g.trace = persistent ? g_trace : nullptr;
+  g.dbg = persistent ? g_dbg : 0;
   g.drop_thresh = 0; g.drop_scale = 1.f; g.drop_site = p.drop_site; g.drop_seed = p.drop_seed.value;
   g.drop_seed_ptr = reinterpret_cast<const unsigned long long*>(p.drop_seed.ptr);
   if (p.drop_p > 0.f) {
@@ -189,12 +231,23 @@ static int gemm_launch_2cta(const GemmProblem& p, int BN, cudaStream_t st) {
     g.drop_scale = 1.0f / (1.0f - p.drop_p);
   }
   const int m_pairs = (p.M + 2 * BM - 1) / (2 * BM);
+  g.tiles_m = m_pairs; g.tiles_n = (p.N + BN - 1) / BN; g.splits = splits;
+  if (persistent) {
+    if (BN == 256) return launch2p_majors<256, 4, 8>(p.a_mn, p.b_mn, ta, tb, g, st);
+    return launch2p_majors<128, 6, 8>(p.a_mn, p.b_mn, ta, tb, g, st);
+  }
   dim3 grid(2 * m_pairs, (p.N + BN - 1) / BN, splits);      // x = M tiles (pair-adjacent), y = N tiles
   if (BN == 256) return launch2_majors<256, 5>(p.a_mn, p.b_mn, ta, tb, g, grid, st);
   return launch2_majors<128, 4>(p.a_mn, p.b_mn, ta, tb, g, grid, st);
 }
 
 int gemm_launch(const GemmProblem& p, cudaStream_t st) {
+  static bool env_read = false;
+  if (!env_read) {            // tuning override for whole-model measurements: MAGB200_GEMM_CFG=<cfg>
+    env_read = true;
+    const char* e = getenv("MAGB200_GEMM_CFG");
+    if (e && *e && g_cfg == 0 && g_dbg == 0) { const int v = atoi(e); g_cfg = v % 100; g_dbg = v / 100; }
+  }
   MAGB_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem %dx%dx%d", p.M, p.N, p.K);
   const bool a32 = p.a_dtype == DT_F32, b32 = p.b_dtype == DT_F32;
   // measured on B200: tcgen05.mma kind::f16 traps (illegal instruction) when A and B formats differ,
@@ -213,6 +266,12 @@ int gemm_launch(const GemmProblem& p, cudaStream_t st) {
   // wgrads); for K = 768 the epilogue and tile quantisation dominate and the 1-CTA kernel with two co-resident
   // CTAs per SM is as fast.  cfg 5 forces 1-CTA, cfg 7 forces 256x128 pairs, cfg 8 256x256 pairs where N allows.
   const bool pair_ok = EB == 2 && p.n_split <= 0 && p.N % 128 == 0;
+  // cfg 9: persistent pair kernel everywhere (256x256 tiles where N is a multiple of 256 and >= 1024, else 256x128);
+  // cfg 10: persistent with 256x128 tiles only.
+  if (pair_ok && (g_cfg == 9 || g_cfg == 10)) {
+    const int bn2 = (g_cfg == 9 && p.N % 256 == 0 && p.N >= 1024) ? 256 : 128;
+    return gemm_launch_2cta(p, bn2, st, true);
+  }
   if (pair_ok && (g_cfg == 7 || g_cfg == 8 || (g_cfg == 0 && p.K >= 2048))) {
     const int bn2 = (g_cfg == 8 && p.N % 256 == 0 && p.N >= 1024) ? 256 : 128;
     return gemm_launch_2cta(p, bn2, st);

@@ -53,6 +53,7 @@ struct GemmArgs {
   uint32_t drop_site;
   unsigned long long drop_seed;
   const unsigned long long* drop_seed_ptr;
+  int tiles_m, tiles_n, splits;   // persistent kernel: pair-tiles along M, tiles along N, K splits
   int dbg;   // measurement modes (results are garbage): 1 = MMA issue without waiting for operands,
              // 2 = operand delivery only (no MMA; the consumer releases each stage as soon as it lands)
 };
@@ -145,18 +146,35 @@ __device__ __forceinline__ void stage_out(const uint8_t* stg, int pitch, uint8_t
   }
 }
 
-// acc[32] (this thread's row, columns [n, n+32)) -> v = alpha * acc + bias
-__device__ __forceinline__ void epi_affine(const GemmArgs& g, int n, const uint32_t (&r)[32], float (&v)[32]) {
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * g.alpha;
-  if (g.bias != nullptr) {
-    const float4* b4 = reinterpret_cast<const float4*>(g.bias + n);
+// acc[32] (this thread's row, 32 consecutive columns) -> v = alpha * acc + bias.  `sb` points at the bias of the
+// chunk's first column in SHARED memory (staged by the warp before it waits for the accumulator; a global load here
+// sits in the dependent chain of every chunk: ~400 cycles each), or is null.
+__device__ __forceinline__ void epi_affine(const GemmArgs& g, const float* sb, const uint32_t (&r)[32], float (&v)[32]) {
+  if (sb != nullptr) {
+    const float4* b4 = reinterpret_cast<const float4*>(sb);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float4 b = __ldg(b4 + j);
-      v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+      const float4 b = b4[j];                     // same address in every lane: one broadcast wavefront
+      v[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), g.alpha, b.x);
+      v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), g.alpha, b.y);
+      v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), g.alpha, b.z);
+      v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), g.alpha, b.w);
     }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * g.alpha;
   }
+}
+// stage the bias of columns [n0, n0 + ncols) (ncols <= 256, multiple of 32) into this warp's shared-memory slot
+__device__ __forceinline__ const float* epi_stage_bias(const GemmArgs& g, float* sbias, int n0, int ncols, int lane) {
+  if (g.bias == nullptr) return nullptr;
+  for (int i = lane * 4; i < ncols; i += 128) {
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n0 + i < g.N) b = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + i));     // N is a multiple of 32
+    *reinterpret_cast<float4*>(sbias + i) = b;
+  }
+  __syncwarp();
+  return sbias;
 }
 __device__ __forceinline__ void row_write_f32(uint8_t* row, int c, const float (&v)[32]) {
   float4* d = reinterpret_cast<float4*>(row + c * 128);
@@ -188,110 +206,131 @@ __device__ __forceinline__ void epi_dropout(const GemmArgs& g, int m, int n, flo
   }
 }
 
-// One epilogue warp: rows [m_base, m_base+32) x columns [n0, n0+BN) of the output.
+// One epilogue warp: rows [m_base, m_base+32) x columns [n0, n0+BN) of the output.  `sbias` = epi_stage_bias() result
+// for these columns.  TMEM is drained two 32-column chunks per wait (both tcgen05.ld in flight together).
+struct EpiCtx {
+  int epi; bool aux32, dual16, live; int ncols, m_row, n0, pass;
+  uint8_t* myrow; const float* sbias;
+};
+template <int BN>
+__device__ __forceinline__ void epi_chunk(const GemmArgs& g, const EpiCtx& x, int c, const uint32_t (&r)[32]) {
+  if (!x.live || c * 32 >= x.ncols) return;
+  float v[32];
+  epi_affine(g, x.sbias ? x.sbias + c * 32 : nullptr, r, v);
+  uint8_t* myrow = x.myrow;
+  switch (x.epi) {
+    case EPI_STORE_F32:
+      if (x.aux32) {
+        const float4* a4 = reinterpret_cast<const float4*>(myrow + c * 128);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 a = a4[j];
+          v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+        }
+      }
+      row_write_f32(myrow, c, v);
+      break;
+    case EPI_ATOMIC_F32:
+      row_write_f32(myrow, c, v);
+      break;
+    case EPI_RELU_F32:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      row_write_f32(myrow, c, v);
+      break;
+    case EPI_STORE_F32_F16:
+      if (x.pass == 0) row_write_f32(myrow, c, v);
+      else row_write_16<false>(myrow, c, v);
+      break;
+    case EPI_STORE_F16:
+      row_write_16<false>(myrow, c, v);
+      break;
+    case EPI_STORE_BF16:
+      row_write_16<true>(myrow, c, v);
+      break;
+    case EPI_GELU_F16:
+      if (x.dual16) row_write_16<false>(myrow + BN * 2, c, v);      // pre-activation, upper half of the row
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+      if (g.drop_thresh != 0) epi_dropout(g, x.m_row, x.n0 + c * 32, v);
+      row_write_16<false>(myrow, c, v);
+      break;
+    case EPI_DGELU_F16: {
+      const uint4* u4 = reinterpret_cast<const uint4*>(myrow + c * 64);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 u = u4[j];
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[t]));
+          v[8 * j + 2 * t] *= gelu_erf_grad(f.x);
+          v[8 * j + 2 * t + 1] *= gelu_erf_grad(f.y);
+        }
+      }
+      if (g.drop_thresh != 0) epi_dropout(g, x.m_row, x.n0 + c * 32, v);
+      row_write_16<false>(myrow, c, v);
+    } break;
+    default: break;
+  }
+}
+
 template <int BN>
 __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& g, uint32_t tmem_warp, int m_base, int n0,
-                                                   uint8_t* stg, int lane, unsigned long long* tr) {
+                                                   uint8_t* stg, int lane, unsigned long long* tr,
+                                                   const float* sbias = nullptr) {
+  static_assert(BN % 64 == 0, "chunks are drained in pairs");
   constexpr int PITCH = EpiStage<BN>::PITCH;
   const int rows = min(32, g.M - m_base);                   // may be <= 0 for a tail tile
   const int ncols = min(BN, g.N - n0);                      // multiple of 32
-  const bool live = rows > 0 && ncols > 0;
-  uint8_t* myrow = stg + lane * PITCH;
-  const int epi = g.epi;
+  EpiCtx x;
+  x.epi = g.epi;
+  x.live = rows > 0 && ncols > 0;
+  x.ncols = ncols; x.m_row = m_base + lane; x.n0 = n0;
+  x.myrow = stg + lane * PITCH;
+  x.sbias = sbias;
+  if (tr) tr[0] = clock64();      // debug stamps: [0] entry, [1] first accumulator chunks in registers, [2] staged, [3] stored
   // -------- auxiliary input through the staging tile (coalesced)
-  const bool aux32 = (epi == EPI_STORE_F32) && g.aux != nullptr;
-  const bool aux16 = (epi == EPI_DGELU_F16);
-  if (live && (aux32 || aux16)) {
-    const int es = aux32 ? 4 : 2;
+  x.aux32 = (x.epi == EPI_STORE_F32) && g.aux != nullptr;
+  const bool aux16 = (x.epi == EPI_DGELU_F16);
+  if (x.live && (x.aux32 || aux16)) {
+    const int es = x.aux32 ? 4 : 2;
     stage_in(stg, PITCH, reinterpret_cast<const uint8_t*>(g.aux) + ((size_t)m_base * g.ldo + n0) * es,
              (size_t)g.ldo * es, rows, ncols * es, lane);
   }
   __syncwarp();
   // GELU with both outputs (g16 and the pre-activation u16 the backward needs): both are fp16, so the two staged
   // tiles fit side by side in the warp's region (2 x BN*2 B <= BN*4 B per row) and one TMEM pass produces both.
-  const bool dual16 = (epi == EPI_GELU_F16 && g.out1 != nullptr);
-  const int npass = epi == EPI_STORE_F32_F16 ? 2 : 1;
+  x.dual16 = (x.epi == EPI_GELU_F16 && g.out1 != nullptr);
+  const int npass = x.epi == EPI_STORE_F32_F16 ? 2 : 1;
   for (int pass = 0; pass < npass; ++pass) {
+    x.pass = pass;
     // which output this pass produces, and its element size
     int es = 4;
     void* out = g.out0;
-    if (epi == EPI_STORE_F16 || epi == EPI_STORE_BF16 || epi == EPI_DGELU_F16 || epi == EPI_GELU_F16) es = 2;
-    if (epi == EPI_STORE_F32_F16) { es = pass == 0 ? 4 : 2; out = pass == 0 ? g.out0 : g.out1; }
+    if (x.epi == EPI_STORE_F16 || x.epi == EPI_STORE_BF16 || x.epi == EPI_DGELU_F16 || x.epi == EPI_GELU_F16) es = 2;
+    if (x.epi == EPI_STORE_F32_F16) { es = pass == 0 ? 4 : 2; out = pass == 0 ? g.out0 : g.out1; }
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_warp + (uint32_t)(c * 32), r);      // warp-collective: executed by every lane
+    for (int c = 0; c < BN / 32; c += 2) {
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32(tmem_warp + (uint32_t)(c * 32), r0);      // warp-collective: executed by every lane
+      tmem_ld_32x32(tmem_warp + (uint32_t)(c * 32 + 32), r1);
       tmem_ld_wait();
-      if (tr && c < 4) tr[52 + c] = clock64();
-      if (!live || c * 32 >= ncols) continue;
-      float v[32];
-      epi_affine(g, n0 + c * 32, r, v);
-      switch (epi) {
-        case EPI_STORE_F32:
-          if (aux32) {
-            const float4* a4 = reinterpret_cast<const float4*>(myrow + c * 128);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 a = a4[j];
-              v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
-            }
-          }
-          row_write_f32(myrow, c, v);
-          break;
-        case EPI_ATOMIC_F32:
-          row_write_f32(myrow, c, v);
-          break;
-        case EPI_RELU_F32:
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          row_write_f32(myrow, c, v);
-          break;
-        case EPI_STORE_F32_F16:
-          if (pass == 0) row_write_f32(myrow, c, v);
-          else row_write_16<false>(myrow, c, v);
-          break;
-        case EPI_STORE_F16:
-          row_write_16<false>(myrow, c, v);
-          break;
-        case EPI_STORE_BF16:
-          row_write_16<true>(myrow, c, v);
-          break;
-        case EPI_GELU_F16:
-          if (dual16) row_write_16<false>(myrow + BN * 2, c, v);      // pre-activation, upper half of the row
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-          if (g.drop_thresh != 0) epi_dropout(g, m_base + lane, n0 + c * 32, v);
-          row_write_16<false>(myrow, c, v);
-          break;
-        case EPI_DGELU_F16: {
-          const uint4* u4 = reinterpret_cast<const uint4*>(myrow + c * 64);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 u = u4[j];
-            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[t]));
-              v[8 * j + 2 * t] *= gelu_erf_grad(f.x);
-              v[8 * j + 2 * t + 1] *= gelu_erf_grad(f.y);
-            }
-          }
-          if (g.drop_thresh != 0) epi_dropout(g, m_base + lane, n0 + c * 32, v);
-          row_write_16<false>(myrow, c, v);
-        } break;
-        default: break;
-      }
+      if (tr && c == 0) tr[1] = clock64();
+      epi_chunk<BN>(g, x, c, r0);
+      epi_chunk<BN>(g, x, c + 1, r1);
     }
     __syncwarp();
-    if (tr) tr[56] = clock64();
-    if (live) {
+    if (tr) tr[2] = clock64();
+    if (x.live) {
       stage_out(stg, PITCH, reinterpret_cast<uint8_t*>(out) + ((size_t)m_base * g.ldo + n0) * es, (size_t)g.ldo * es,
-                rows, ncols * es, lane, epi == EPI_ATOMIC_F32);
-      if (dual16)
+                rows, ncols * es, lane, x.epi == EPI_ATOMIC_F32);
+      if (x.dual16)
         stage_out(stg + BN * 2, PITCH, reinterpret_cast<uint8_t*>(g.out1) + ((size_t)m_base * g.ldo + n0) * 2,
                   (size_t)g.ldo * 2, rows, ncols * 2, lane, false);
     }
     __syncwarp();
+    if (tr) tr[3] = clock64();
   }
 }
 
@@ -302,7 +341,10 @@ struct GemmSmem {
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+  static constexpr int BIAS_OFFSET = BAR_OFFSET + 128;                          // barriers + TMEM slot fit in 128 B
+  static constexpr int BIAS_BYTES = 4 * BN * 4;                                 // one bias copy per epilogue warp
+  static constexpr int TOTAL = BIAS_OFFSET + BIAS_BYTES + 1024;                 // + alignment slack
+  static_assert((2 * STAGES + 1) * 8 + 4 <= 128, "barrier area");
 };
 
 // CL = cluster size along N (1 or 2).  With CL = 2 the two CTAs of a cluster compute adjacent N tiles of the same
@@ -455,15 +497,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const float* sb = epi_stage_bias(g, reinterpret_cast<float*>(smem + SM::BIAS_OFFSET) + q * BN, n0, BN, lane);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     if (tr && threadIdx.x == 64) tr[60] = clock64();
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
     // the accumulator is complete => every TMA load has landed and every MMA has read its operands:
     // the pipeline stages are idle and serve as this warp's staging tile
     static_assert(4 * EpiStage<BN>::WARP_BYTES <= STAGES * SM::STAGE_BYTES, "staging does not fit in the pipeline smem");
     gemm_epilogue_warp<BN>(g, tmem_base + ((uint32_t)(q * 32) << 16), m0 + q * 32, n0,
-                           smem + q * EpiStage<BN>::WARP_BYTES, lane, threadIdx.x == 64 ? tr : nullptr);
+                           smem + q * EpiStage<BN>::WARP_BYTES, lane, (tr && threadIdx.x == 64) ? tr + 52 : nullptr, sb);
     if (tr && threadIdx.x == 64) tr[61] = clock64();
   }
   tc_fence_before();
@@ -490,7 +533,10 @@ struct Gemm2Smem {
   static constexpr int B_BYTES = (BN / 2) * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;
+  static constexpr int BIAS_OFFSET = BAR_OFFSET + 128;
+  static constexpr int BIAS_BYTES = 4 * BN * 4;
+  static constexpr int TOTAL = BIAS_OFFSET + BIAS_BYTES + 1024;
+  static_assert((2 * STAGES + 1) * 8 + 4 <= 128, "barrier area");
 };
 
 template <bool A_MN, bool B_MN, int BN, int STAGES>
@@ -604,16 +650,234 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
   } else {
     // ------------------------------------------------------------------ epilogue (both CTAs, warps 2..5)
+    const int q = warp & 3;
+    const float* sb = epi_stage_bias(g, reinterpret_cast<float*>(smem + SM::BIAS_OFFSET) + q * BN, n0, BN, lane);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    const int q = warp & 3;
     gemm_epilogue_warp<BN>(g, tmem_base + ((uint32_t)(q * 32) << 16), m0 + q * 32, n0,
-                           smem + q * EpiStage<BN>::WARP_BYTES, lane, nullptr);
+                           smem + q * EpiStage<BN>::WARP_BYTES, lane, nullptr, sb);
   }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                      // both CTAs are done with TMEM and with each other's barriers
   if (warp == 1) tmem_dealloc_2sm(tmem_base, BN);
+}
+
+// ================================================================================================
+// Persistent 2-CTA kernel.  One cluster (SM pair) per resident slot walks the tile list
+//   tile t -> (m pair = t % tiles_m, n tile = (t / tiles_m) % tiles_n, K split = t / (tiles_m * tiles_n)),
+// t = cluster id, cluster id + #clusters, ...   The accumulator is double-buffered in TMEM (2 x BN columns), so the
+// epilogue of tile i (NEPI warps per CTA, each with a private staging tile) overlaps the main loop of tile i+1, and
+// the TMA/MMA ring never drains between tiles.  Why: the main loop of this model's GEMMs is bound by L2->SM
+// operand delivery (~6 KB/clk chip-wide, measured with the "delivery only" mode), a 256x256 pair tile needs half
+// the operand bytes per flop of four 128x128 tiles -- but only pays off when its long epilogue is hidden.
+//   full_bar[s]   (leader's)  : as in the one-shot kernel
+//   empty_bar[s]  (per CTA)   : multicast tcgen05.commit
+//   tmem_full[b]  (per CTA)   : multicast tcgen05.commit after the last K block of the tile using buffer b
+//   tmem_empty[b] (leader's)  : 2 * NEPI arrivals (every epilogue warp of both CTAs) once buffer b has been read
+template <int BN, int STAGES, int NEPI>
+struct Gemm2pSmem {
+  static constexpr int A_BYTES = 128 * 128;
+  static constexpr int B_BYTES = (BN / 2) * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SUB = 64;                                   // columns per epilogue sub-block
+  static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int STG_BYTES = NEPI * EpiStage<SUB>::WARP_BYTES;
+  static constexpr int BAR_OFFSET = STG_OFFSET + STG_BYTES;
+  static constexpr int BIAS_OFFSET = BAR_OFFSET + 256;
+  static constexpr int BIAS_BYTES = 4 * BN * 4;                     // NEPI warps x BN / (NEPI / 4) columns
+  static constexpr int TOTAL = BIAS_OFFSET + BIAS_BYTES + 1024;
+  static_assert((2 * STAGES + 4) * 8 + 4 <= 256, "barrier area");
+};
+
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+template <bool A_MN, bool B_MN, int BN, int STAGES, int NEPI>
+__global__ void __launch_bounds__(64 + 32 * NEPI, 1)
+gemm2p_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+  using T = GemmTile<2>;
+  using SM = Gemm2pSmem<BN, STAGES, NEPI>;
+  static_assert(BN == 128 || BN == 256, "BN");
+  static_assert(NEPI == 4 || NEPI == 8, "NEPI");
+  constexpr int TCOLS = 2 * BN;                        // two accumulator buffers
+  constexpr int WCOLS = BN / (NEPI / 4);               // columns one epilogue warp drains per tile
+  static_assert(WCOLS % SM::SUB == 0, "epilogue column split");
+  static_assert(SM::TOTAL <= 232448, "shared memory");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;            // [2]
+  uint64_t* tmem_empty = tmem_full + 2;                // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int tiles_mn = g.tiles_m * g.tiles_n;
+  const int total = tiles_mn * g.splits;
+  unsigned long long* tr = g.trace ? g.trace + 64ull * blockIdx.x : nullptr;   // debug: clock64 stamps per CTA
+  if (tr && threadIdx.x == 0) tr[0] = clock64();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&tmem_full[b], 1);
+        mbar_init(&tmem_empty[b], 2 * NEPI);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc_2sm(tmem_slot, TCOLS);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (tr && threadIdx.x == 0) tr[1] = clock64();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = cluster_id; tile < total; tile += num_clusters) {
+        const int mp = tile % g.tiles_m, r = tile / g.tiles_m;
+        const int nt = r % g.tiles_n, z = r / g.tiles_n;
+        const int m0 = (2 * mp + (int)crank) * T::BM;
+        const int nb0 = nt * BN + (int)crank * (BN / 2);            // this CTA's half of the B tile
+        const int kb_begin = z * g.kb_per_split;
+        const int kb_end = min(kb_begin + g.kb_per_split, g.kb_total);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * SM::STAGE_BYTES);
+          const uint32_t bar = mapa_shared(&full_bar[stage], 0);
+          uint8_t* a_dst = smem + stage * SM::STAGE_BYTES;
+          uint8_t* b_dst = a_dst + SM::A_BYTES;
+          const int k0 = kb * T::BK;
+          if constexpr (!A_MN) {
+            tma_load_2d_2sm(a_dst, &tmA, bar, k0, m0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < T::BM / T::ATOM; ++i)
+              tma_load_2d_2sm(a_dst + i * (T::BK * 128), &tmA, bar, m0 + i * T::ATOM, k0);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d_2sm(b_dst, &tmB, bar, k0, nb0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < (BN / 2) / T::ATOM; ++i)
+              tma_load_2d_2sm(b_dst + i * (T::BK * 128), &tmB, bar, nb0 + i * T::ATOM, k0);
+          }
+          if (tr && it < 12) tr[2 + it] = clock64();
+          ++it;
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader && lane == 0) {
+      const uint32_t sb16 = smem_u32(smem) >> 4;
+      const uint32_t dhi = smem_desc_hi_sw128(1024);
+      constexpr uint32_t A_LBO = A_MN ? T::BK * 128 : 0, B_LBO = B_MN ? T::BK * 128 : 0;
+      constexpr uint32_t A_KSTEP = A_MN ? T::UK * 128 : 32, B_KSTEP = B_MN ? T::UK * 128 : 32;
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t acc_it = 0;
+      int it = 0;
+      const uint32_t peer_empty = mapa_shared(&empty_bar[0], 1), peer_tfull = mapa_shared(&tmem_full[0], 1);
+      for (int tile = cluster_id; tile < total; tile += num_clusters, ++acc_it) {
+        const int z = tile / tiles_mn;
+        const int kb_begin = z * g.kb_per_split;
+        const int num_kb = min(kb_begin + g.kb_per_split, g.kb_total) - kb_begin;
+        const uint32_t buf = acc_it & 1, acc_phase = (acc_it >> 1) & 1;
+        mbar_wait(&tmem_empty[buf], acc_phase ^ 1);      // epilogue warps of both CTAs have drained this buffer
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          if (g.dbg != 1) mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (tr && it < 12) tr[14 + it] = clock64();
+          if (g.dbg == 2) {          // delivery only: release the stage in both CTAs without touching the tensor core
+            mbar_arrive(&empty_bar[stage]);
+            mbar_arrive_cluster(peer_empty + stage * 8);
+            ++it;
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          const uint32_t soff = (uint32_t)stage * SM::STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < T::BK / T::UK; ++k) {
+            const uint64_t adesc = smem_desc_from(dhi, sb16 + ((soff + k * A_KSTEP) >> 4), A_LBO);
+            const uint64_t bdesc = smem_desc_from(dhi, sb16 + ((soff + SM::A_BYTES + k * B_KSTEP) >> 4), B_LBO);
+            tc_mma_f16_2sm(d_tmem, adesc, bdesc, g.idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit_2sm(&empty_bar[stage]);
+          if (tr && it < 12) tr[26 + it] = clock64();
+          ++it;
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (g.dbg == 2) {
+          mbar_arrive(&tmem_full[buf]);
+          mbar_arrive_cluster(peer_tfull + buf * 8);
+        } else {
+          tc_commit_2sm(&tmem_full[buf]);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (both CTAs, warps 2 .. 2+NEPI-1)
+    const int ew = warp - 2;
+    const int q = warp & 3;                              // TMEM lane quarter this warp may access
+    const int cg = ew >> 2;                              // column group (NEPI == 8: two warps share a lane quarter)
+    uint8_t* stg = smem + SM::STG_OFFSET + ew * EpiStage<SM::SUB>::WARP_BYTES;
+    const uint32_t empty_remote = mapa_shared(&tmem_empty[0], 0);
+    uint32_t acc_it = 0;
+    for (int tile = cluster_id; tile < total; tile += num_clusters, ++acc_it) {
+      const int mp = tile % g.tiles_m, r = tile / g.tiles_m;
+      const int nt = r % g.tiles_n;
+      const uint32_t buf = acc_it & 1, acc_phase = (acc_it >> 1) & 1;
+      const float* sbw = epi_stage_bias(g, reinterpret_cast<float*>(smem + SM::BIAS_OFFSET) + ew * WCOLS,
+                                        nt * BN + cg * WCOLS, WCOLS, lane);
+      mbar_wait(&tmem_full[buf], acc_phase);
+      tc_fence_after();
+      if (tr && threadIdx.x == 64 && acc_it < 3) tr[38 + 2 * acc_it] = clock64();
+      const int m_base = (2 * mp + (int)crank) * T::BM + q * 32;
+#pragma unroll 1
+      for (int sb = 0; sb < WCOLS / SM::SUB; ++sb) {
+        const int col = cg * WCOLS + sb * SM::SUB;
+        gemm_epilogue_warp<SM::SUB>(g, tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + col, m_base, nt * BN + col,
+                                    stg, lane, (tr && threadIdx.x == 64 && acc_it == 0 && sb < 2) ? tr + 44 + 4 * sb : nullptr,
+                                    sbw ? sbw + sb * SM::SUB : nullptr);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (tr && threadIdx.x == 64 && acc_it < 3) tr[39 + 2 * acc_it] = clock64();
+      if (lane == 0) mbar_arrive_cluster(empty_remote + buf * 8);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_2sm(tmem_base, TCOLS);
+  if (tr && threadIdx.x == 0) tr[63] = clock64();
 }
 
 #endif  // __CUDACC__
