@@ -121,6 +121,24 @@ __device__ __forceinline__ uint32_t mapa_shared(const void* p, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
   return r;
 }
+// ---------------------------------------------------------------------------- warp-uniform single-lane issue
+// The TMA / tcgen05 instructions take their operands from UNIFORM registers.  Issued from inside `if (lane == 0)`
+// the compiler has to treat every operand as divergent and wraps each instruction in ELECT + 4 x R2UR.BROADCAST +
+// a BRA.U.ANY loop (seen in SASS; measured ~200 cycles per TMA load and ~80 per MMA, which made both single-thread
+// loops the bottleneck of the main loop).  Instead the whole warp walks the loop in uniform control flow -- warp index
+// obtained through a shuffle so the compiler can prove it uniform -- and only the issue itself is predicated on one
+// elected lane.
+__device__ __forceinline__ int warp_idx_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------------------- clusters
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

@@ -367,7 +367,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_idx_uniform();
   const int lane = threadIdx.x & 31;
   unsigned long long* tr = g.trace ? g.trace + 64ull * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) : nullptr;
   if (tr && threadIdx.x == 0) tr[0] = clock64();
@@ -400,7 +400,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   if constexpr (CL > 1) cluster_sync_all();   // peer barriers are initialised before anything is multicast to them
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
   constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1);
   if (tr && threadIdx.x == 0) tr[1] = clock64();
@@ -409,14 +409,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   // ring revolutions, inner loop unrolled over STAGES): shared-memory addresses, barrier addresses and the UMMA
   // descriptors are then "base + constant", one uniform add each, instead of a dependent chain per instruction.
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (whole warp, one lane issues)
+    {
       for (int base = 0; base < num_kb; base += STAGES) {
         const uint32_t ph = (base / STAGES) & 1;
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
           if (base + s < num_kb) {
             mbar_wait(&empty_bar[s], ph ^ 1);
+            if (elect_one_sync()) {
             mbar_arrive_expect_tx(&full_bar[s], SM::STAGE_BYTES);
             uint8_t* a_dst = smem + s * SM::STAGE_BYTES;
             uint8_t* b_dst = a_dst + SM::A_BYTES;
@@ -450,13 +451,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 tma_load_2d(b_dst + i * (T::BK * 128), &tmB, &full_bar[s], n0 + i * T::ATOM, k0);
             }
             if (tr && base + s < 16) tr[2 + base + s] = clock64();
+            }
+            __syncwarp();
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp, one lane issues)
+    {
       const uint32_t sb16 = smem_u32(smem) >> 4;
       const uint32_t dhi = smem_desc_hi_sw128(1024);
       // K-major : 8-row groups 1024 B apart (SBO); K advances 32 B inside the 128-B swizzle row.
@@ -471,12 +474,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (base + s < num_kb) {
             if (g.dbg != 1) mbar_wait(&full_bar[s], ph);
             tc_fence_after();
+            if (elect_one_sync()) {
             if (tr && base + s < 16) tr[20 + base + s] = clock64();
             if (g.dbg == 2) {
               mbar_arrive(&empty_bar[s]);
               if (tr && base + s < 16) tr[40 + base + s] = clock64();
-              continue;
-            }
+            } else {
 #pragma unroll
             for (int k = 0; k < T::BK / T::UK; ++k) {
               const uint64_t adesc = smem_desc_from(dhi, sb16 + ((s * SM::STAGE_BYTES + k * A_KSTEP) >> 4), A_LBO);
@@ -489,11 +492,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if constexpr (CL == 1) tc_commit(&empty_bar[s]);  // smem slot reusable once these MMAs have read it
             else tc_commit_mc(&empty_bar[s], kMask);          // ... in every CTA that multicasts into it
             if (tr && base + s < 16) tr[40 + base + s] = clock64();
+            }
+            }
+            __syncwarp();
           }
         }
       }
-      if (g.dbg == 2) mbar_arrive(tmem_full_bar);
-      else tc_commit(tmem_full_bar);    // accumulator complete
+      if (elect_one_sync()) {
+        if (g.dbg == 2) mbar_arrive(tmem_full_bar);
+        else tc_commit(tmem_full_bar);    // accumulator complete
+      }
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
@@ -554,9 +563,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_idx_uniform();
   const int lane = threadIdx.x & 31;
-  const uint32_t crank = cluster_ctarank();          // 0 = leader; the pair is adjacent along grid x (cluster 2x1x1):
+  const uint32_t crank = __shfl_sync(0xffffffffu, cluster_ctarank(), 0);   // 0 = leader; the pair is adjacent along grid x (cluster 2x1x1):
   const bool leader = crank == 0;                    // cta_group::2 pairs CTAs of consecutive cluster rank
   const int m0 = blockIdx.x * T::BM;                 // this CTA's 128 rows (pair: blockIdx.x = 2p, 2p+1)
   const int n0 = blockIdx.y * BN;
@@ -586,11 +595,11 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   __syncthreads();
   cluster_sync_all();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs; one lane issues)
+    {
       const int nb0 = n0 + (int)crank * (BN / 2);      // this CTA's half of the B tile
       for (int base = 0; base < num_kb; base += STAGES) {
         const uint32_t ph = (base / STAGES) & 1;
@@ -598,6 +607,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int s = 0; s < STAGES; ++s) {
           if (base + s < num_kb) {
             mbar_wait(&empty_bar[s], ph ^ 1);
+            if (elect_one_sync()) {
             if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * SM::STAGE_BYTES);   // bytes of both CTAs
             const uint32_t bar = mapa_shared(&full_bar[s], 0);                       // the leader's barrier
             uint8_t* a_dst = smem + s * SM::STAGE_BYTES;
@@ -617,13 +627,15 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               for (int i = 0; i < (BN / 2) / T::ATOM; ++i)
                 tma_load_2d_2sm(b_dst + i * (T::BK * 128), &tmB, bar, nb0 + i * T::ATOM, k0);
             }
+            }
+            __syncwarp();
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (leader && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only; one lane issues)
+    if (leader) {
       const uint32_t sb16 = smem_u32(smem) >> 4;
       const uint32_t dhi = smem_desc_hi_sw128(1024);
       constexpr uint32_t A_LBO = A_MN ? T::BK * 128 : 0, B_LBO = B_MN ? T::BK * 128 : 0;
@@ -635,6 +647,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           if (base + s < num_kb) {
             mbar_wait(&full_bar[s], ph);
             tc_fence_after();
+            if (elect_one_sync()) {
 #pragma unroll
             for (int k = 0; k < T::BK / T::UK; ++k) {
               const uint64_t adesc = smem_desc_from(dhi, sb16 + ((s * SM::STAGE_BYTES + k * A_KSTEP) >> 4), A_LBO);
@@ -643,10 +656,13 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               tc_mma_f16_2sm(tmem_base, adesc, bdesc, g.idesc, (s | k) != 0 ? 1u : (uint32_t)(base != 0));
             }
             tc_commit_2sm(&empty_bar[s]);
+            }
+            __syncwarp();
           }
         }
       }
-      tc_commit_2sm(tmem_full_bar);
+      if (elect_one_sync()) tc_commit_2sm(tmem_full_bar);
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------------ epilogue (both CTAs, warps 2..5)
@@ -714,9 +730,9 @@ gemm2p_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   uint64_t* tmem_empty = tmem_full + 2;                // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_idx_uniform();
   const int lane = threadIdx.x & 31;
-  const uint32_t crank = cluster_ctarank();
+  const uint32_t crank = __shfl_sync(0xffffffffu, cluster_ctarank(), 0);
   const bool leader = crank == 0;
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
   const int tiles_mn = g.tiles_m * g.tiles_n;
@@ -748,12 +764,12 @@ gemm2p_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   __syncthreads();
   cluster_sync_all();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   if (tr && threadIdx.x == 0) tr[1] = clock64();
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs; one lane issues)
+    {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -766,6 +782,7 @@ gemm2p_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const int kb_end = min(kb_begin + g.kb_per_split, g.kb_total);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (elect_one_sync()) {
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * SM::STAGE_BYTES);
           const uint32_t bar = mapa_shared(&full_bar[stage], 0);
           uint8_t* a_dst = smem + stage * SM::STAGE_BYTES;
@@ -786,14 +803,16 @@ gemm2p_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
               tma_load_2d_2sm(b_dst + i * (T::BK * 128), &tmB, bar, nb0 + i * T::ATOM, k0);
           }
           if (tr && it < 12) tr[2 + it] = clock64();
+          }
+          __syncwarp();
           ++it;
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (leader && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only; one lane issues)
+    if (leader) {
       const uint32_t sb16 = smem_u32(smem) >> 4;
       const uint32_t dhi = smem_desc_hi_sw128(1024);
       constexpr uint32_t A_LBO = A_MN ? T::BK * 128 : 0, B_LBO = B_MN ? T::BK * 128 : 0;
@@ -814,14 +833,12 @@ gemm2p_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         for (int kb = 0; kb < num_kb; ++kb) {
           if (g.dbg != 1) mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (elect_one_sync()) {
           if (tr && it < 12) tr[14 + it] = clock64();
           if (g.dbg == 2) {          // delivery only: release the stage in both CTAs without touching the tensor core
             mbar_arrive(&empty_bar[stage]);
             mbar_arrive_cluster(peer_empty + stage * 8);
-            ++it;
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-            continue;
-          }
+          } else {
           const uint32_t soff = (uint32_t)stage * SM::STAGE_BYTES;
 #pragma unroll
           for (int k = 0; k < T::BK / T::UK; ++k) {
@@ -831,15 +848,21 @@ gemm2p_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           }
           tc_commit_2sm(&empty_bar[stage]);
           if (tr && it < 12) tr[26 + it] = clock64();
+          }
+          }
+          __syncwarp();
           ++it;
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (g.dbg == 2) {
-          mbar_arrive(&tmem_full[buf]);
-          mbar_arrive_cluster(peer_tfull + buf * 8);
-        } else {
-          tc_commit_2sm(&tmem_full[buf]);
+        if (elect_one_sync()) {
+          if (g.dbg == 2) {
+            mbar_arrive(&tmem_full[buf]);
+            mbar_arrive_cluster(peer_tfull + buf * 8);
+          } else {
+            tc_commit_2sm(&tmem_full[buf]);
+          }
         }
+        __syncwarp();
       }
     }
   } else {
