@@ -12,6 +12,7 @@
 // softmax reduction.  Backward works on the TRANSPOSED score tile (keys x queries): each warp owns 16
 // keys and accumulates dV, dK for them over all queries (no cross-warp reduction), stores dS to shared
 // memory, and after one barrier each warp produces dQ for its 16 queries.
+#include <stdlib.h>
 #include "common.cuh"
 #include "host.h"
 
@@ -475,6 +476,229 @@ __global__ void __launch_bounds__(128) sdpa_bwd_mma_kernel(const __half* __restr
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Backward with 8 warps per (head, batch element).  The 4-warp kernel above is latency bound (ncu: issue active
+// 30 %, ~3 warps per scheduler): here warp w = (key block kb = w & 3, half hq = w >> 2) owns a quarter of the work
+//   phase 1: S^T, dP^T for 16 keys x 32 queries (query half hq)  -> Pd^T, dS^T (fp16, [key][query]) and dS ([query][key])
+//            go to shared memory; Pd^T / dS^T reuse the V / dO tiles, which are dead once every warp has left phase 1
+//   phase 2: dV, dK for 16 keys x 32 head dims (dim half hq), reduction over all 64 queries from shared memory
+//   phase 3: dQ for 16 queries (block kb) x 32 head dims
+template <int NT>
+__device__ __forceinline__ void colsum_part(const float (&acc)[NT][4], float* sacc, int g, int t, bool row0_ok, bool row1_ok) {
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    float s0 = (row0_ok ? acc[nt][0] : 0.f) + (row1_ok ? acc[nt][2] : 0.f);
+    float s1 = (row0_ok ? acc[nt][1] : 0.f) + (row1_ok ? acc[nt][3] : 0.f);
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    if (g == 0) {
+      atomicAdd(sacc + nt * 8 + 2 * t, s0);
+      atomicAdd(sacc + nt * 8 + 2 * t + 1, s1);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) sdpa_bwd_mma8_kernel(const __half* __restrict__ qkv, const __half* __restrict__ dctx,
+                                                            const __half* __restrict__ ctx, const float* __restrict__ lse,
+                                                            const int64_t* __restrict__ mask, int S, int heads,
+                                                            uint32_t thresh, float dscale, Seed seed_in, uint32_t site,
+                                                            float oscale, __half* __restrict__ dqkv,
+                                                            float* __restrict__ dbias) {
+  const uint64_t seed = seed_in.ptr ? *seed_in.ptr : seed_in.value;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int kb = warp & 3, hq = warp >> 2;
+  const int Hd = heads * D, ld = 3 * Hd;
+  const __half* base = qkv + (int64_t)b * S * ld + h * D;
+  const __half* dObase = dctx + (int64_t)b * S * Hd + h * D;
+  load_tile_async(base, ld, S, sm.q);
+  load_tile_async(base + Hd, ld, S, sm.k);
+  load_tile_async(base + 2 * Hd, ld, S, sm.v);
+  load_tile_async(dObase, Hd, S, sm.dO);
+  for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) sm.bias[i] = 0.f;
+  if (thresh != 0) fill_keep_bits(sm.keep, seed, site, ((uint64_t)b * heads + h) * S * S, S * S, thresh);
+  if (threadIdx.x < 2 * SP) {
+    // D[q] = sum_d dO[q][d] * O[q][d]: two threads per query (32 head dims each), 16-byte loads
+    const int i = threadIdx.x >> 1, half = threadIdx.x & 1;
+    float acc = 0.f;
+    if (i < S) {
+      const __half* o = ctx + ((int64_t)b * S + i) * Hd + h * D + half * 32;
+      const __half* d = dObase + (int64_t)i * Hd + half * 32;
+      uint4 ov[4], dv[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        ov[c] = *reinterpret_cast<const uint4*>(o + c * 8);
+        dv[c] = *reinterpret_cast<const uint4*>(d + c * 8);
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const __half2* oh = reinterpret_cast<const __half2*>(&ov[c]);
+        const __half2* dh = reinterpret_cast<const __half2*>(&dv[c]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 a = __half22float2(oh[k]), e = __half22float2(dh[k]);
+          acc += a.x * e.x + a.y * e.y;
+        }
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (half == 0) {
+      sm.Dq[i] = acc;
+      sm.lse[i] = i < S ? lse[((int64_t)b * heads + h) * S + i] : 0.f;
+    }
+  }
+  async_wait_all();
+  __syncthreads();
+  transpose_tile(sm.q, sm.qt);
+  transpose_tile(sm.k, sm.kt);
+  transpose_tile(sm.dO, sm.dOt);
+  __syncthreads();
+  const int64_t* mrow = mask ? mask + (int64_t)b * S : nullptr;
+  const int r0 = kb * 16;
+  const int k0 = r0 + g, k1 = r0 + g + 8;            // this thread's two key rows (phase 1/2) or query rows (phase 3)
+  const int nb = hq * 4;                             // first 8-wide n-tile of this warp's half
+  __half* obase = dqkv + (int64_t)b * S * ld + h * D;
+  const bool active = r0 < S;
+
+  // ---- phase 1: S^T = K Q^T and dPd^T = V dO^T for (16 keys) x (32 queries)
+  float st[4][4], pd[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    st[j][0] = st[j][1] = st[j][2] = st[j][3] = 0.f;
+    pd[j][0] = pd[j][1] = pd[j][2] = pd[j][3] = 0.f;
+  }
+  if (active) {
+    float dp[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t ak[4], av[4];
+      frag_a(sm.k, r0, kk * 16, g, t, ak);
+      frag_a(sm.v, r0, kk * 16, g, t, av);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t bq[2], bo[2];
+        frag_b(sm.q, (nb + j) * 8, kk * 16, g, t, bq);       // B[k = d][n = query] = Q[query][d]
+        frag_b(sm.dO, (nb + j) * 8, kk * 16, g, t, bo);
+        mma16816(st[j], ak[0], ak[1], ak[2], ak[3], bq[0], bq[1]);
+        mma16816(dp[j], av[0], av[1], av[2], av[3], bo[0], bo[1]);
+      }
+    }
+    const float m0 = k0 < S ? mask_add(mrow, k0) : 0.f, m1 = k1 < S ? mask_add(mrow, k1) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int key = (e < 2) ? k0 : k1;
+        const int qi = (nb + j) * 8 + 2 * t + (e & 1);
+        float dsv = 0.f, pdv = 0.f;
+        if (key < S && qi < S) {
+          const float p = expf(st[j][e] * 0.125f + ((e < 2) ? m0 : m1) - sm.lse[qi]);
+          const float ds = thresh == 0 ? 1.f : (keep_bit(sm.keep, qi * S + key) ? dscale : 0.f);
+          pdv = p * ds;
+          dsv = p * (dp[j][e] * ds - sm.Dq[qi]) * 0.125f;      // includes d(score)/d(qk) = 1/sqrt(64)
+        }
+        pd[j][e] = pdv;
+        st[j][e] = dsv;                                          // st now holds dS^T
+      }
+    }
+  }
+  __syncthreads();                                   // every warp is done reading the V and dO tiles
+  __half* pdT = sm.v;                                // [key][query]
+  __half* dsT = sm.dO;                               // [key][query]
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int q0 = (nb + j) * 8 + 2 * t;
+      *reinterpret_cast<uint32_t*>(pdT + k0 * PITCH + q0) = packh(pd[j][0], pd[j][1]);
+      *reinterpret_cast<uint32_t*>(pdT + k1 * PITCH + q0) = packh(pd[j][2], pd[j][3]);
+      *reinterpret_cast<uint32_t*>(dsT + k0 * PITCH + q0) = packh(st[j][0], st[j][1]);
+      *reinterpret_cast<uint32_t*>(dsT + k1 * PITCH + q0) = packh(st[j][2], st[j][3]);
+      sm.dS[q0 * PITCH + k0] = __float2half_rn(st[j][0]);
+      sm.dS[(q0 + 1) * PITCH + k0] = __float2half_rn(st[j][1]);
+      sm.dS[q0 * PITCH + k1] = __float2half_rn(st[j][2]);
+      sm.dS[(q0 + 1) * PITCH + k1] = __float2half_rn(st[j][3]);
+    }
+  } else {
+    // keys >= S: the dS columns of this key block are zero (for this warp's 32 queries)
+    for (int i = lane; i < 32 * 16; i += 32) sm.dS[(hq * 32 + (i >> 4)) * PITCH + r0 + (i & 15)] = __float2half_rn(0.f);
+  }
+  __syncthreads();
+
+  if (active) {
+    // ---- phase 2: dV = Pd^T dO, dK = dS^T Q for (16 keys) x (32 head dims), reduction over the 64 queries
+    float dv[4][4], dk[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      dv[j][0] = dv[j][1] = dv[j][2] = dv[j][3] = 0.f;
+      dk[j][0] = dk[j][1] = dk[j][2] = dk[j][3] = 0.f;
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t ap[4], as[4];
+      frag_a(pdT, r0, kk * 16, g, t, ap);
+      frag_a(dsT, r0, kk * 16, g, t, as);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t bo[2], bq[2];
+        frag_b(sm.dOt, (nb + j) * 8, kk * 16, g, t, bo);     // B[k = query][n = d] = dOt[d][query]
+        frag_b(sm.qt, (nb + j) * 8, kk * 16, g, t, bq);
+        mma16816(dv[j], ap[0], ap[1], ap[2], ap[3], bo[0], bo[1]);
+        mma16816(dk[j], as[0], as[1], as[2], as[3], bq[0], bq[1]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int d = (nb + j) * 8 + 2 * t;
+      if (k0 < S) {
+        *reinterpret_cast<uint32_t*>(obase + (int64_t)k0 * ld + Hd + d) = packh(dk[j][0], dk[j][1]);
+        *reinterpret_cast<uint32_t*>(obase + (int64_t)k0 * ld + 2 * Hd + d) = packh(dv[j][0], dv[j][1]);
+      }
+      if (k1 < S) {
+        *reinterpret_cast<uint32_t*>(obase + (int64_t)k1 * ld + Hd + d) = packh(dk[j][2], dk[j][3]);
+        *reinterpret_cast<uint32_t*>(obase + (int64_t)k1 * ld + 2 * Hd + d) = packh(dv[j][2], dv[j][3]);
+      }
+    }
+    if (dbias != nullptr) {
+      colsum_part<4>(dk, sm.bias + D + nb * 8, g, t, k0 < S, k1 < S);
+      colsum_part<4>(dv, sm.bias + 2 * D + nb * 8, g, t, k0 < S, k1 < S);
+    }
+    // ---- phase 3: dQ = dS K for (16 queries) x (32 head dims)
+    float dq[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t a[4];
+      frag_a(sm.dS, r0, kk * 16, g, t, a);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t bb[2];
+        frag_b(sm.kt, (nb + j) * 8, kk * 16, g, t, bb);      // B[k = key][n = d] = Kt[d][key]
+        mma16816(dq[j], a[0], a[1], a[2], a[3], bb[0], bb[1]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int d = (nb + j) * 8 + 2 * t;
+      if (k0 < S) *reinterpret_cast<uint32_t*>(obase + (int64_t)k0 * ld + d) = packh(dq[j][0], dq[j][1]);
+      if (k1 < S) *reinterpret_cast<uint32_t*>(obase + (int64_t)k1 * ld + d) = packh(dq[j][2], dq[j][3]);
+    }
+    if (dbias != nullptr) colsum_part<4>(dq, sm.bias + nb * 8, g, t, k0 < S, k1 < S);
+  }
+  if (dbias != nullptr) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * D; i += blockDim.x)
+      atomicAdd(dbias + (i / D) * Hd + h * D + (i % D), sm.bias[i] * oscale);
+  }
+}
+
 inline void drop_params(float p, uint32_t& thresh, float& scale) {
   if (p <= 0.f) { thresh = 0; scale = 1.f; return; }
   double t = (double)p * 4294967296.0;
@@ -502,13 +726,22 @@ int sdpa_bwd_mma(const __half* qkv, const __half* dctx, const __half* ctx, const
   uint32_t th; float ds;
   drop_params(p, th, ds);
   static bool configured = false;
+  static bool four_warps = false;
   if (!configured) {
     MAGB_CHECK_CUDA(cudaFuncSetAttribute(sdpa_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(BwdSmem)));
+    MAGB_CHECK_CUDA(cudaFuncSetAttribute(sdpa_bwd_mma8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(BwdSmem)));
+    const char* e = getenv("MAGB200_SDPA_BWD_WARPS");      // 4 = the original one-key-block-per-warp kernel
+    four_warps = e && e[0] == '4';
     configured = true;
   }
-  sdpa_bwd_mma_kernel<<<dim3(heads, B), 128, sizeof(BwdSmem), st>>>(qkv, dctx, ctx, lse, mask, S, heads, th, ds, seed,
-                                                                   site, oscale, dqkv, dbias);
+  if (four_warps)
+    sdpa_bwd_mma_kernel<<<dim3(heads, B), 128, sizeof(BwdSmem), st>>>(qkv, dctx, ctx, lse, mask, S, heads, th, ds, seed,
+                                                                     site, oscale, dqkv, dbias);
+  else
+    sdpa_bwd_mma8_kernel<<<dim3(heads, B), 256, sizeof(BwdSmem), st>>>(qkv, dctx, ctx, lse, mask, S, heads, th, ds, seed,
+                                                                      site, oscale, dqkv, dbias);
   MAGB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

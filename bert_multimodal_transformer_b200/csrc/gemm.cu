@@ -124,6 +124,7 @@ static int launch_majors(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUte
 static unsigned long long* g_trace = nullptr;
 static int g_cfg = 0;
 static int g_dbg = 0;
+static int g_policy = 1;   // roles routed to the persistent pair kernel by default: forward Linears (profiles/r01_gemm_policy.txt)
 void gemm_set_debug(unsigned long long* trace, int cfg) { g_trace = trace; g_cfg = cfg % 100; g_dbg = cfg / 100; }
 
 // ---------------------------------------------------------------------------------------------
@@ -247,6 +248,8 @@ int gemm_launch(const GemmProblem& p, cudaStream_t st) {
     env_read = true;
     const char* e = getenv("MAGB200_GEMM_CFG");
     if (e && *e && g_cfg == 0 && g_dbg == 0) { const int v = atoi(e); g_cfg = v % 100; g_dbg = v / 100; }
+    const char* pol = getenv("MAGB200_GEMM_POLICY");
+    if (pol && *pol) g_policy = atoi(pol);
   }
   MAGB_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem %dx%dx%d", p.M, p.N, p.K);
   const bool a32 = p.a_dtype == DT_F32, b32 = p.b_dtype == DT_F32;
@@ -268,6 +271,12 @@ int gemm_launch(const GemmProblem& p, cudaStream_t st) {
   const bool pair_ok = EB == 2 && p.n_split <= 0 && p.N % 128 == 0;
   // cfg 9: persistent pair kernel everywhere (256x256 tiles where N is a multiple of 256 and >= 1024, else 256x128);
   // cfg 10: persistent with 256x128 tiles only.
+  // default policy (cfg 0): persistent pair kernel for the roles in g_policy (bit 0 forward, bit 1 dgrad, bit 2 wgrad;
+  // MAGB200_GEMM_POLICY overrides) -- measured per role in profiles/r01_gemm_policy.txt
+  if (pair_ok && g_cfg == 0 && ((g_policy >> p.role) & 1)) {
+    const int bn2 = (p.N % 256 == 0 && p.N >= 1024) ? 256 : 128;
+    return gemm_launch_2cta(p, bn2, st, true);
+  }
   if (pair_ok && (g_cfg == 9 || g_cfg == 10)) {
     const int bn2 = (g_cfg == 9 && p.N % 256 == 0 && p.N >= 1024) ? 256 : 128;
     return gemm_launch_2cta(p, bn2, st, true);

@@ -35,6 +35,7 @@ struct GemmProblem {
   float drop_p = 0.f;
   Seed drop_seed;
   uint32_t drop_site = 0;
+  int role = 0;              // scheduling hint: 0 = forward Linear, 1 = dgrad, 2 = wgrad (kernel selection policy)
 };
 
 int gemm_launch(const GemmProblem& p, cudaStream_t stream);

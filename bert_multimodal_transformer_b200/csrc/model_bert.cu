@@ -156,6 +156,7 @@ int linear_dgrad(const __half* dY, int ldy, const __half* W, int ldw, int M, int
   GemmProblem p;
   p.A = dY; p.B = W; p.M = M; p.N = Kin; p.K = Nout; p.lda = ldy; p.ldb = ldw; p.b_mn = true;
   p.a_dtype = DT_F16; p.b_dtype = DT_F16; p.epi = epi; p.out0 = out0; p.aux = aux; p.ldo = ldo;
+  p.role = 1;
   return gemm_launch(p, st);
 }
 // dW[Nout,Kin] += dY[T,Nout]^T * X[T,Kin] : both operands token-major, read in place (MN-major)
@@ -164,6 +165,7 @@ int linear_wgrad(const __half* dY, int ldy, const __half* X, int ldx, int T, int
   GemmProblem p;
   p.A = dY; p.B = X; p.M = Nout; p.N = Kin; p.K = T; p.lda = ldy; p.ldb = ldx; p.a_mn = true; p.b_mn = true;
   p.a_dtype = DT_F16; p.b_dtype = DT_F16; p.epi = EPI_ATOMIC_F32; p.out0 = dW; p.ldo = lddw; p.splits = splits; p.alpha = oscale;
+  p.role = 2;
   return gemm_launch(p, st);
 }
 

@@ -440,25 +440,40 @@ __global__ void __launch_bounds__(128) dropout_residual_ln_fwd_kernel(
 //   dz   (fp32)  : gradient wrt the LayerNorm input = gradient of the residual branch
 //   dpre (fp16)  : dropout-masked dz = gradient wrt the GEMM output (operand of dgrad / wgrad GEMMs)
 //   dgamma, dbeta, dbias (+= column sums)
-__global__ void __launch_bounds__(128) ln_bwd_kernel(const float* __restrict__ dy32, const float* __restrict__ y32,
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy32, const float* __restrict__ y32,
                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                      const float* __restrict__ rstd_in, uint32_t thresh, float scale,
                                                      Seed seed_in, uint32_t site, int T, float oscale,
                                                      float* __restrict__ dz32, __half* __restrict__ dpre,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                      float* __restrict__ dbias) {
+  // One block of 8 warps per SM (the three register accumulators cap occupancy anyway); a warp walks rows
+  // t, t + 8*grid, ... with the NEXT row's two loads already in flight while it works on the current one.
   const uint64_t seed = seed_in.ptr ? *seed_in.ptr : seed_in.value;
-  __shared__ float red[4 * H];
+  __shared__ float red[8 * H];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   Row g, b, accg, accb, accp;
   load_row(g, gamma, lane);
   load_row(b, beta, lane);
   row_zero(accg); row_zero(accb); row_zero(accp);
-  for (int t = blockIdx.x * 4 + warp; t < T; t += gridDim.x * 4) {
-    Row dy, xh;
+  const int stride = gridDim.x * 8;
+  int t = blockIdx.x * 8 + warp;
+  Row dy, xh;
+  float rstd = 0.f;
+  if (t < T) {
     load_row(dy, dy32 + (int64_t)t * H, lane);
     load_row(xh, y32 + (int64_t)t * H, lane);
-    const float rstd = rstd_in[t];
+    rstd = rstd_in[t];
+  }
+  while (t < T) {
+    const int tn = t + stride;
+    Row dyn, xhn;
+    float rstdn = 0.f;
+    if (tn < T) {
+      load_row(dyn, dy32 + (int64_t)tn * H, lane);
+      load_row(xhn, y32 + (int64_t)tn * H, lane);
+      rstdn = rstd_in[tn];
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < 4 * VEC; ++i) {
@@ -478,10 +493,16 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const float* __restrict__ d
 #pragma unroll
     for (int i = 0; i < 4 * VEC; ++i) accp.v[i] += dy.v[i];
     store_row_f16(dy, dpre + (int64_t)t * H, lane);
+    if (tn < T) {
+#pragma unroll
+      for (int i = 0; i < 4 * VEC; ++i) { dy.v[i] = dyn.v[i]; xh.v[i] = xhn.v[i]; }
+      rstd = rstdn;
+    }
+    t = tn;
   }
-  block_reduce_flush<4>(accg, red, dgamma, oscale, warp, lane);
-  block_reduce_flush<4>(accb, red, dbeta, oscale, warp, lane);
-  if (dbias) block_reduce_flush<4>(accp, red, dbias, oscale, warp, lane);
+  block_reduce_flush<8>(accg, red, dgamma, oscale, warp, lane);
+  block_reduce_flush<8>(accb, red, dbeta, oscale, warp, lane);
+  if (dbias) block_reduce_flush<8>(accp, red, dbias, oscale, warp, lane);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -643,6 +664,10 @@ static int grid_rows(int T) {
   int g = (T + 3) / 4;
   return g < 296 ? g : 296;  // 2 x 148 SMs; each warp then loops over rows
 }
+static int grid_rows_8w(int T) {
+  int g = (T + 7) / 8;
+  return g < 148 ? g : 148;  // 8 warps per block, one block per SM
+}
 static int grid_rows_1x(int T) {
   int g = (T + 3) / 4;
   return g < 148 ? g : 148;  // one block per SM: fewer global atomics at the end
@@ -705,7 +730,7 @@ int ln_bwd(const float* dy32, const float* y32, const float* gamma, const float*
            float* dbias, cudaStream_t st) {
   uint32_t th; float sc;
   drop_params(p, th, sc);
-  ln_bwd_kernel<<<grid_rows(T), 128, 0, st>>>(dy32, y32, gamma, beta, rstd, th, sc, seed, site, T, oscale, dz32, dpre,
+  ln_bwd_kernel<<<grid_rows_8w(T), 256, 0, st>>>(dy32, y32, gamma, beta, rstd, th, sc, seed, site, T, oscale, dz32, dpre,
                                               dgamma, dbeta, dbias);
   MAGB_CHECK_CUDA(cudaGetLastError());
   count_launch();

@@ -8,7 +8,7 @@ print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e']['value'
 timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_model.py -x -q 2>&1 | tail -3 | cut -c1-300
 if [ ${PIPESTATUS[0]} -ne 0 ]; then echo "tests failed: skipping the benches"; exit 1; fi
 for cfg in ${CFGS:-0}; do
-  MAGB200_GEMM_CFG=$cfg timeout 600 python bench.py --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/bench_cfg$cfg.log 2>&1; rc=$?; echo "bench cfg=$cfg exit=$rc"
+  MAGB200_GEMM_POLICY=$cfg timeout 600 python bench.py --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/bench_cfg$cfg.log 2>&1; rc=$?; echo "bench policy=$cfg exit=$rc"
   if [ $rc -ne 0 ]; then tail -5 gpurun_out/bench_cfg$cfg.log | cut -c1-300; exit 1; fi
   summ gpurun_out/bench_cfg$cfg.log
 done
