@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(128) sdpa_fwd_mma_kernel(const __half* __restr
                                                            const int64_t* __restrict__ mask, int S, int heads,
                                                            uint32_t thresh, float dscale, Seed seed_in, uint32_t site,
                                                            __half* __restrict__ ctx, float* __restrict__ lse) {
+  pdl_trigger();   // the next kernel in the stream (a GEMM) may start its private prologue
   const uint64_t seed = seed_in.ptr ? *seed_in.ptr : seed_in.value;
   __shared__ __align__(16) __half sQ[SP * PITCH];
   __shared__ __align__(16) __half sK[SP * PITCH];
@@ -297,6 +298,7 @@ __global__ void __launch_bounds__(128) sdpa_bwd_mma_kernel(const __half* __restr
                                                            uint32_t thresh, float dscale, Seed seed_in, uint32_t site,
                                                            float oscale, __half* __restrict__ dqkv,
                                                            float* __restrict__ dbias) {
+  pdl_trigger();   // the next kernel in the stream (a GEMM) may start its private prologue
   const uint64_t seed = seed_in.ptr ? *seed_in.ptr : seed_in.value;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
@@ -507,6 +509,7 @@ __global__ void __launch_bounds__(256) sdpa_bwd_mma8_kernel(const __half* __rest
                                                             uint32_t thresh, float dscale, Seed seed_in, uint32_t site,
                                                             float oscale, __half* __restrict__ dqkv,
                                                             float* __restrict__ dbias) {
+  pdl_trigger();   // the next kernel in the stream (a GEMM) may start its private prologue
   const uint64_t seed = seed_in.ptr ? *seed_in.ptr : seed_in.value;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);

@@ -139,6 +139,14 @@ __device__ __forceinline__ bool elect_one_sync() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the
+// stream is still draining: its CTAs run their private prologue (barrier init, TMEM allocation, descriptor prefetch),
+// then block in pdl_wait() until the predecessor has completed and its writes are visible.  pdl_trigger() in the
+// predecessor allows that early start once all of ITS CTAs are resident.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------- clusters
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

@@ -86,6 +86,20 @@ static int get_tensor_map(CUtensorMap* out, const void* ptr, int dtype, uint64_t
   return 0;
 }
 
+// Programmatic dependent launch for every GEMM (the kernels call griddepcontrol.wait after their private prologue);
+// MAGB200_PDL=0 turns the attribute off.
+static int pdl_attr(cudaLaunchAttribute* a) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("MAGB200_PDL");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!enabled) return 0;
+  a->id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  a->val.programmaticStreamSerializationAllowed = 1;
+  return 1;
+}
+
 template <int EB, bool A_MN, bool B_MN, int BN, int STAGES, int CL>
 static int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, dim3 grid, cudaStream_t st) {
   using SM = GemmSmem<EB, A_MN, B_MN, BN, STAGES>;
@@ -95,15 +109,18 @@ static int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const Ge
     MAGB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
     configured = true;
   }
-  if (CL == 1) {
-    kern<<<grid, 192, SM::TOTAL, st>>>(ta, tb, g);
-  } else {
+  {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = SM::TOTAL; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (CL > 1) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = CL; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+      ++na;
+    }
+    na += pdl_attr(attr + na);
+    cfg.attrs = attr; cfg.numAttrs = na;
     MAGB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, g));
   }
   MAGB_CHECK_CUDA(cudaGetLastError());
@@ -140,10 +157,10 @@ static int launch2_variant(const CUtensorMap& ta, const CUtensorMap& tb, const G
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = SM::TOTAL; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1 + pdl_attr(attr + 1);
   MAGB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, g));
   MAGB_CHECK_CUDA(cudaGetLastError());
   count_launch();
@@ -169,10 +186,10 @@ static int launch2p_variant(const CUtensorMap& ta, const CUtensorMap& tb, const 
   MAGB_REQUIRE(dev >= 0 && dev < 16, "gemm: device index %d out of range", dev);
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(64 + 32 * NEPI); cfg.dynamicSmemBytes = SM::TOTAL; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1 + pdl_attr(attr + 1);
   if (max_clusters[dev] == 0) {
     MAGB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
     cudaDeviceProp prop;

@@ -401,6 +401,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if constexpr (CL > 1) cluster_sync_all();   // peer barriers are initialised before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_wait();        // everything above is private to the CTA; operands / bias / aux may come from the previous kernel
+  pdl_trigger();
   const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
   constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1);
   if (tr && threadIdx.x == 0) tr[1] = clock64();
@@ -596,6 +598,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs; one lane issues)
@@ -765,6 +769,8 @@ gemm2p_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_wait();
+  pdl_trigger();
   if (tr && threadIdx.x == 0) tr[1] = clock64();
 
   if (warp == 0) {

@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(128) cls_bwd_kernel(const float* __restrict__ 
                                                       float scale, Seed seed_in, uint32_t site, float oscale,
                                                       __half* __restrict__ dpre, float* __restrict__ dWc,
                                                       float* __restrict__ dbc) {
+  pdl_trigger();   // the next kernel in the stream (a GEMM) may start its private prologue
   const uint64_t seed = seed_in.ptr ? *seed_in.ptr : seed_in.value;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * 4 + warp;

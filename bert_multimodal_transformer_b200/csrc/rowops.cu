@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(128) embed_ln_fwd_kernel(
     const float* __restrict__ type, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
     uint32_t thresh, float scale, Seed seed_in, uint32_t site, int V, int A, int KA, int T, int S, int vocab,
     float* __restrict__ emb32, __half* __restrict__ amag) {
+  pdl_trigger();   // the next kernel in the stream (a GEMM) may start its private prologue
   const uint64_t seed = seed_in.ptr ? *seed_in.ptr : seed_in.value;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * 4 + warp;
@@ -312,6 +313,7 @@ __global__ void __launch_bounds__(128) mag_tail_fwd_kernel(const float* __restri
                                                            float eps, uint32_t thresh, float scale, Seed seed_in,
                                                            uint32_t site, int T, float* __restrict__ out32,
                                                            __half* __restrict__ out16) {
+  pdl_trigger();   // the next kernel in the stream (a GEMM) may start its private prologue
   const uint64_t seed = seed_in.ptr ? *seed_in.ptr : seed_in.value;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * 4 + warp;
@@ -339,6 +341,7 @@ __global__ void __launch_bounds__(128) mag_tail_bwd_kernel(
     const float* __restrict__ gamma, float beta_shift, float eps, uint32_t thresh, float scale, Seed seed_in,
     uint32_t site, int T, float oscale, __half* __restrict__ dG, float* __restrict__ dtext,
     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias4) {
+  pdl_trigger();   // the next kernel in the stream (a GEMM) may start its private prologue
   const uint64_t seed = seed_in.ptr ? *seed_in.ptr : seed_in.value;
   __shared__ float acc[6 * H];   // dgamma | dbeta | dbias of the four gate-GEMM column blocks
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -414,6 +417,7 @@ __global__ void __launch_bounds__(128) dropout_residual_ln_fwd_kernel(
     const float* __restrict__ pre, const float* __restrict__ res, const float* __restrict__ gamma,
     const float* __restrict__ beta, float eps, uint32_t thresh, float scale, Seed seed_in, uint32_t site, int T,
     float* __restrict__ y32, __half* __restrict__ y16, float* __restrict__ rstd_out) {
+  pdl_trigger();   // the next kernel in the stream (a GEMM) may start its private prologue
   const uint64_t seed = seed_in.ptr ? *seed_in.ptr : seed_in.value;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * 4 + warp;
@@ -447,6 +451,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
                                                      float* __restrict__ dz32, __half* __restrict__ dpre,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                      float* __restrict__ dbias) {
+  pdl_trigger();   // the next kernel in the stream (a GEMM) may start its private prologue
   // One block of 8 warps per SM (the three register accumulators cap occupancy anyway); a warp walks rows
   // t, t + 8*grid, ... with the NEXT row's two loads already in flight while it works on the current one.
   const uint64_t seed = seed_in.ptr ? *seed_in.ptr : seed_in.value;
@@ -509,6 +514,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
 // out[n] += sum_t in[t][n]   (bias gradients of the QKV and FFN-in projections), fp16 input
 __global__ void __launch_bounds__(256) colsum_f16_kernel(const __half* __restrict__ in, int T, int N, float oscale,
                                                          float* __restrict__ out) {
+  pdl_trigger();   // the next kernel in the stream (a GEMM) may start its private prologue
   // block = 8 warps; a warp covers 256 columns (16 B per lane); warps and blockIdx.y split the rows
   __shared__ float red[8][256];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

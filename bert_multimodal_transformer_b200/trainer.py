@@ -148,14 +148,15 @@ class MagBertTrainer:
             self.host_loss[slot].copy_(self.loss, non_blocking=True)
 
     def _backward_overlapped(self, i):
-        """Backward in 3 pieces; the gradient range of each finished group of layers is all-reduced on a side
+        """Backward in pieces (MAGB200_ALLREDUCE_GROUPS layer groups, default 6); the gradient range of each finished group of layers is all-reduced on a side
         stream while the next piece computes (bucketed overlap).  The order of the flat buffer
         is [embeddings | layer 0 .. L-1 | pooler, MAG, classifier], so a group of layers is one contiguous slice."""
         eng = self.eng
         main = torch.cuda.current_stream(self.dev)
         side = self.comm_stream
         Ln = eng.layers
-        cuts = sorted({Ln, (2 * Ln) // 3, Ln // 3, 0}, reverse=True)          # e.g. 12, 8, 4, 0
+        ng = max(1, min(Ln, int(os.environ.get("MAGB200_ALLREDUCE_GROUPS", "6"))))
+        cuts = sorted({(k * Ln) // ng for k in range(ng + 1)}, reverse=True)  # e.g. 12, 10, 8, 6, 4, 2, 0
         groups = [(cuts[k + 1], cuts[k]) for k in range(len(cuts) - 1)]       # [(8,12), (4,8), (0,4)]
         args = (self.train_dims, self.ws, i["input_ids"], i["token_type_ids"], i["attention_mask"], self.dlogits,
                 self.grads)

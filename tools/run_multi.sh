@@ -1,9 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
 N=${1:-2}
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29601 tools/ddp_check.py > gpurun_out/ddp_check_$N.log 2>&1; echo "ddp_check exit=$?"
+timeout 180 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29601 tools/ddp_check.py > gpurun_out/ddp_check_$N.log 2>&1; echo "ddp_check exit=$?"
 grep -E "DDP_CHECK|max_abs|spread|Error|error" gpurun_out/ddp_check_$N.log | cut -c1-600 | tail -8
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29602 bench.py --gpus $N --steps 60 --warmup 5 --no-cpu-baseline > gpurun_out/bench_n$N.log 2>&1; echo "bench exit=$?"
+timeout 180 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29602 bench.py --gpus $N --steps 60 --warmup 5 --no-cpu-baseline > gpurun_out/bench_n$N.log 2>&1; echo "bench exit=$?"
 grep '"metric"' gpurun_out/bench_n$N.log | python -c "
 import json,sys
 try:
