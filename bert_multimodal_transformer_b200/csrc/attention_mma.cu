@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(128) sdpa_fwd_mma_kernel(const __half* __restr
                                                            const int64_t* __restrict__ mask, int S, int heads,
                                                            uint32_t thresh, float dscale, Seed seed_in, uint32_t site,
                                                            __half* __restrict__ ctx, float* __restrict__ lse) {
+  pdl_wait();      // may be launched with the PDL attribute: the predecessor can still be running
   pdl_trigger();   // the next kernel in the stream (a GEMM) may start its private prologue
   const uint64_t seed = seed_in.ptr ? *seed_in.ptr : seed_in.value;
   __shared__ __align__(16) __half sQ[SP * PITCH];
@@ -509,6 +510,7 @@ __global__ void __launch_bounds__(256) sdpa_bwd_mma8_kernel(const __half* __rest
                                                             uint32_t thresh, float dscale, Seed seed_in, uint32_t site,
                                                             float oscale, __half* __restrict__ dqkv,
                                                             float* __restrict__ dbias) {
+  pdl_wait();      // may be launched with the PDL attribute: the predecessor can still be running
   pdl_trigger();   // the next kernel in the stream (a GEMM) may start its private prologue
   const uint64_t seed = seed_in.ptr ? *seed_in.ptr : seed_in.value;
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -716,7 +718,8 @@ int sdpa_fwd_mma(const __half* qkv, const int64_t* mask, int B, int S, int heads
   MAGB_REQUIRE(S >= 1 && S <= SP, "sdpa_fwd_mma: S=%d out of range", S);
   uint32_t th; float ds;
   drop_params(p, th, ds);
-  sdpa_fwd_mma_kernel<<<dim3(heads, B), 128, 0, st>>>(qkv, mask, S, heads, th, ds, seed, site, ctx, lse);
+  MAGB_CHECK_CUDA(launch_pdl(sdpa_fwd_mma_kernel, dim3(heads, B), dim3(128), 0, st, qkv, mask, S, heads, th, ds, seed, site, ctx,
+                             lse));
   MAGB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -743,8 +746,8 @@ int sdpa_bwd_mma(const __half* qkv, const __half* dctx, const __half* ctx, const
     sdpa_bwd_mma_kernel<<<dim3(heads, B), 128, sizeof(BwdSmem), st>>>(qkv, dctx, ctx, lse, mask, S, heads, th, ds, seed,
                                                                      site, oscale, dqkv, dbias);
   else
-    sdpa_bwd_mma8_kernel<<<dim3(heads, B), 256, sizeof(BwdSmem), st>>>(qkv, dctx, ctx, lse, mask, S, heads, th, ds, seed,
-                                                                      site, oscale, dqkv, dbias);
+    MAGB_CHECK_CUDA(launch_pdl(sdpa_bwd_mma8_kernel, dim3(heads, B), dim3(256), sizeof(BwdSmem), st, qkv, dctx, ctx, lse, mask, S, heads, th, ds, seed,
+                                                                      site, oscale, dqkv, dbias));
   MAGB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -1,3 +1,4 @@
+#include <stdlib.h>
 // extern "C" boundary: error reporting + the generic GEMM entry point.
 #include "common.cuh"
 #include "host.h"
@@ -16,6 +17,14 @@ void set_last_error(const char* fmt, ...) {
   va_end(ap);
 }
 static unsigned long long g_launches = 0;
+int pdl_level() {
+  static int level = -1;
+  if (level < 0) {
+    const char* e = getenv("MAGB200_PDL");
+    level = (e && *e) ? atoi(e) : 1;
+  }
+  return level;
+}
 void count_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
 }  // namespace magb200
 

@@ -35,6 +35,21 @@ void count_launch();   // every kernel launch of the library bumps a process-wid
     }                                                           \
   } while (0)
 
+// Programmatic dependent launch level (MAGB200_PDL): 0 = off, 1 = the GEMMs (default), 2 = also the LayerNorm /
+// attention / column-sum kernels between them.  launch_pdl() is only for kernels that call pdl_wait() before their
+// first access to global memory.
+int pdl_level();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_level() >= 2 ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ----------------------------------------------------------------------------------------
 // element type tags shared between host API and kernels
 enum DType : int { DT_F32 = 0, DT_F16 = 1, DT_BF16 = 2 };

@@ -89,12 +89,7 @@ static int get_tensor_map(CUtensorMap* out, const void* ptr, int dtype, uint64_t
 // Programmatic dependent launch for every GEMM (the kernels call griddepcontrol.wait after their private prologue);
 // MAGB200_PDL=0 turns the attribute off.
 static int pdl_attr(cudaLaunchAttribute* a) {
-  static int enabled = -1;
-  if (enabled < 0) {
-    const char* e = getenv("MAGB200_PDL");
-    enabled = (e && e[0] == '0') ? 0 : 1;
-  }
-  if (!enabled) return 0;
+  if (pdl_level() < 1) return 0;
   a->id = cudaLaunchAttributeProgrammaticStreamSerialization;
   a->val.programmaticStreamSerializationAllowed = 1;
   return 1;

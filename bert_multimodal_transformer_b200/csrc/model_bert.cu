@@ -32,7 +32,7 @@ struct Carve {
 };
 
 struct LayerWs {
-  __half* qkv16; __half* ctx16; float* a32; __half* a16; __half* u16; __half* g16; float* rstd1; float* rstd2;
+  __half* qkv16; __half* ctx16; float* a32; __half* a16; __half* gp16; __half* g16; float* rstd1; float* rstd2;
   float* lse;
 };
 
@@ -68,7 +68,7 @@ BertWs carve_ws(const magb200_bert_dims& d, void* base) {
     L.ctx16 = c.take<__half>(T * H);
     L.a32 = c.take<float>(T * H);
     L.a16 = c.take<__half>(T * H);
-    L.u16 = c.take<__half>(T * I);
+    L.gp16 = c.take<__half>(T * I);
     L.g16 = c.take<__half>(T * I);
     L.rstd1 = c.take<float>(T);
     L.rstd2 = c.take<float>(T);
@@ -218,7 +218,7 @@ int bert_forward(const magb200_bert_dims& d, const int64_t* off, const float* P,
                    nullptr, H, st));
     RUN(dropout_residual_ln_fwd(w.pre32, w.x32[l], P + o[MAGB200_LOFF_LN1_W], P + o[MAGB200_LOFF_LN1_B], d.ln_eps,
                                 d.p_hidden, sd, site_attn_out(l), T, L.a32, L.a16, L.rstd1, st));
-    RUN(linear_fwd(L.a16, H, P16 + o[MAGB200_LOFF_F1_W], T, I, H, P + o[MAGB200_LOFF_F1_B], EPI_GELU_F16, L.g16, L.u16,
+    RUN(linear_fwd(L.a16, H, P16 + o[MAGB200_LOFF_F1_W], T, I, H, P + o[MAGB200_LOFF_F1_B], EPI_GELU_F16, L.g16, L.gp16,
                    I, st));
     RUN(linear_fwd(L.g16, I, P16 + o[MAGB200_LOFF_F2_W], T, H, I, P + o[MAGB200_LOFF_F2_B], EPI_STORE_F32, w.pre32,
                    nullptr, H, st));
@@ -322,7 +322,7 @@ int bert_backward_part(const magb200_bert_dims& d, const int64_t* off, const flo
                G + o[MAGB200_LOFF_F2_B], st));
     RUN(fork());
     RUN(linear_wgrad(dpre_f, H, L.g16, I, T, H, I, G + o[MAGB200_LOFF_F2_W], I, 1, us, sst));
-    RUN(linear_dgrad(dpre_f, H, P16 + o[MAGB200_LOFF_F2_W], I, T, I, H, EPI_DGELU_F16, du, L.u16, I, st));
+    RUN(linear_dgrad(dpre_f, H, P16 + o[MAGB200_LOFF_F2_W], I, T, I, H, EPI_DGELU_F16, du, L.gp16, I, st));
     // BertIntermediate: gelu(dense(a))
     RUN(fork());
     RUN(colsum_f16(du, T, I, us, G + o[MAGB200_LOFF_F1_B], sst));

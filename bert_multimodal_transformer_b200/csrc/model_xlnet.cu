@@ -29,7 +29,7 @@ struct Carve {
 };
 
 struct XLayerWs {
-  __half* qkv16; __half* kr16; __half* ctx16; float* a32; __half* a16; __half* u16; __half* g16; float* rstd1; float* rstd2;
+  __half* qkv16; __half* kr16; __half* ctx16; float* a32; __half* a16; __half* gp16; __half* g16; float* rstd1; float* rstd2;
 };
 struct XlWs {
   __half* pos16; __half* amag16; float* G32; float* mag32; __half* mag16;
@@ -65,7 +65,7 @@ XlWs carve_ws(const magb200_xlnet_dims& d, void* base) {
     L.ctx16 = c.take<__half>(T * H);
     L.a32 = c.take<float>(T * H);
     L.a16 = c.take<__half>(T * H);
-    L.u16 = c.take<__half>(T * I);
+    L.gp16 = c.take<__half>(T * I);
     L.g16 = c.take<__half>(T * I);
     L.rstd1 = c.take<float>(T);
     L.rstd2 = c.take<float>(T);
@@ -196,7 +196,7 @@ int xlnet_forward(const magb200_xlnet_dims& d, const int64_t* off, const float* 
     // XLNetFeedForward: layer_1 -> gelu -> dropout -> layer_2 -> dropout -> +residual -> LN
     GemmProblem f1 = gp(L.a16, H, false, P16 + o[MAGB200_XLOFF_F1_W], H, false, T, I, H, EPI_GELU_F16,
                         P + o[MAGB200_XLOFF_F1_B], L.g16, I);
-    f1.out1 = L.u16; f1.drop_p = d.p_drop; f1.drop_seed = sd; f1.drop_site = site_ffn_mid(l);
+    f1.out1 = L.gp16; f1.drop_p = d.p_drop; f1.drop_seed = sd; f1.drop_site = site_ffn_mid(l);
     RUN(gemm_launch(f1, st));
     RUN(gemm_launch(gp(L.g16, I, false, P16 + o[MAGB200_XLOFF_F2_W], I, false, T, H, I, EPI_STORE_F32,
                        P + o[MAGB200_XLOFF_F2_B], w.pre32, H), st));
@@ -252,7 +252,7 @@ int xlnet_backward(const magb200_xlnet_dims& d, const int64_t* off, const float*
                G + o[MAGB200_XLOFF_F2_B], st));
     RUN(wgrad(w.dpre16, H, L.g16, I, T, H, I, G + o[MAGB200_XLOFF_F2_W], I, 1));
     GemmProblem dg = gp(w.dpre16, H, false, P16 + o[MAGB200_XLOFF_F2_W], I, true, T, I, H, EPI_DGELU_F16, nullptr, w.du16, I);
-    dg.aux = L.u16; dg.drop_p = d.p_drop; dg.drop_seed = sd; dg.drop_site = site_ffn_mid(l);
+    dg.aux = L.gp16; dg.drop_p = d.p_drop; dg.drop_seed = sd; dg.drop_site = site_ffn_mid(l);
     RUN(gemm_launch(dg, st));
     RUN(colsum_f16(w.du16, T, I, us, G + o[MAGB200_XLOFF_F1_B], st));
     RUN(wgrad(w.du16, I, L.a16, H, T, I, H, G + o[MAGB200_XLOFF_F1_W], H, 1));

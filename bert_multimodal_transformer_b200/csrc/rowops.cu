@@ -417,6 +417,7 @@ __global__ void __launch_bounds__(128) dropout_residual_ln_fwd_kernel(
     const float* __restrict__ pre, const float* __restrict__ res, const float* __restrict__ gamma,
     const float* __restrict__ beta, float eps, uint32_t thresh, float scale, Seed seed_in, uint32_t site, int T,
     float* __restrict__ y32, __half* __restrict__ y16, float* __restrict__ rstd_out) {
+  pdl_wait();      // may be launched with the PDL attribute: the predecessor can still be running
   pdl_trigger();   // the next kernel in the stream (a GEMM) may start its private prologue
   const uint64_t seed = seed_in.ptr ? *seed_in.ptr : seed_in.value;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -451,6 +452,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
                                                      float* __restrict__ dz32, __half* __restrict__ dpre,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                      float* __restrict__ dbias) {
+  pdl_wait();      // may be launched with the PDL attribute: the predecessor can still be running
   pdl_trigger();   // the next kernel in the stream (a GEMM) may start its private prologue
   // One block of 8 warps per SM (the three register accumulators cap occupancy anyway); a warp walks rows
   // t, t + 8*grid, ... with the NEXT row's two loads already in flight while it works on the current one.
@@ -514,6 +516,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
 // out[n] += sum_t in[t][n]   (bias gradients of the QKV and FFN-in projections), fp16 input
 __global__ void __launch_bounds__(256) colsum_f16_kernel(const __half* __restrict__ in, int T, int N, float oscale,
                                                          float* __restrict__ out) {
+  pdl_wait();      // may be launched with the PDL attribute: the predecessor can still be running
   pdl_trigger();   // the next kernel in the stream (a GEMM) may start its private prologue
   // block = 8 warps; a warp covers 256 columns (16 B per lane); warps and blockIdx.y split the rows
   __shared__ float red[8][256];
@@ -724,8 +727,8 @@ int dropout_residual_ln_fwd(const float* pre, const float* res, const float* gam
                             cudaStream_t st) {
   uint32_t th; float sc;
   drop_params(p, th, sc);
-  dropout_residual_ln_fwd_kernel<<<(T + 3) / 4, 128, 0, st>>>(pre, res, gamma, beta, eps, th, sc, seed, site, T, y32,
-                                                              y16, rstd);
+  MAGB_CHECK_CUDA(launch_pdl(dropout_residual_ln_fwd_kernel, dim3((T + 3) / 4), dim3(128), 0, st, pre, res, gamma, beta, eps,
+                             th, sc, seed, site, T, y32, y16, rstd));
   MAGB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -736,8 +739,8 @@ int ln_bwd(const float* dy32, const float* y32, const float* gamma, const float*
            float* dbias, cudaStream_t st) {
   uint32_t th; float sc;
   drop_params(p, th, sc);
-  ln_bwd_kernel<<<grid_rows_8w(T), 256, 0, st>>>(dy32, y32, gamma, beta, rstd, th, sc, seed, site, T, oscale, dz32, dpre,
-                                              dgamma, dbeta, dbias);
+  MAGB_CHECK_CUDA(launch_pdl(ln_bwd_kernel, dim3(grid_rows_8w(T)), dim3(256), 0, st, dy32, y32, gamma, beta, rstd, th, sc, seed, site, T, oscale, dz32, dpre,
+                                              dgamma, dbeta, dbias));
   MAGB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -750,7 +753,7 @@ int colsum_f16(const __half* in, int T, int N, float oscale, float* out, cudaStr
   if (gy > (T + 31) / 32) gy = (T + 31) / 32;
   if (gy < 1) gy = 1;
   dim3 grid(gx, gy);
-  colsum_f16_kernel<<<grid, 256, 0, st>>>(in, T, N, oscale, out);
+  MAGB_CHECK_CUDA(launch_pdl(colsum_f16_kernel, grid, dim3(256), 0, st, in, T, N, oscale, out));
   MAGB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -32,8 +32,8 @@ extern "C" {
 #define MAGB200_EPI_STORE_F32 0      /* out0(f32) = v (+ aux(f32) when aux != NULL) */
 #define MAGB200_EPI_STORE_F16 1      /* out0(f16) = v */
 #define MAGB200_EPI_STORE_BF16 2     /* out0(bf16) = v */
-#define MAGB200_EPI_GELU_F16 3       /* out0(f16) = gelu_erf(v); out1(f16) = v when out1 != NULL */
-#define MAGB200_EPI_DGELU_F16 4      /* out0(f16) = v * gelu_erf'(aux(f16)) */
+#define MAGB200_EPI_GELU_F16 3       /* out0(f16) = gelu_erf(v); out1(f16) = gelu_erf'(v) when out1 != NULL (saved for backward) */
+#define MAGB200_EPI_DGELU_F16 4      /* out0(f16) = v * aux(f16), aux = the derivative saved by MAGB200_EPI_GELU_F16 */
 #define MAGB200_EPI_ATOMIC_F32 5     /* out0(f32) += v */
 #define MAGB200_EPI_STORE_F32_F16 6  /* out0(f32) = v; out1(f16) = v */
 #define MAGB200_EPI_RELU_F32 7       /* out0(f32) = max(v, 0) */

@@ -61,6 +61,43 @@ def test_gemm(M, N, K, a_mn, b_mn, epi):
     assert (out.double().cpu() - ref).abs().max().item() < tol
 
 
+@pytest.mark.parametrize("M,N,K", [(2400, 3072, 768), (200, 256, 128)])
+def test_gemm_gelu_epilogues(M, N, K):
+    """EPI_GELU_F16 writes gelu(v) and (second output) gelu'(v); EPI_DGELU_F16 multiplies by that saved derivative:
+    together they are BertIntermediate's activation forward/backward (transformers 3.0.2 ACT2FN["gelu"] = erf form)."""
+    g = _g(3)
+    A = (torch.randn(M, K, generator=g) * 0.5).half()
+    B = (torch.randn(N, K, generator=g) * 0.08).half()
+    bias = torch.randn(N, generator=g) * 0.1
+    v = A.double() @ B.double().t() + bias.double()
+    gelu = 0.5 * v * (1 + torch.erf(v / math.sqrt(2)))
+    dgelu = 0.5 * (1 + torch.erf(v / math.sqrt(2))) + v * torch.exp(-0.5 * v * v) / math.sqrt(2 * math.pi)
+    Ad, Bd, bias_d = A.cuda(), B.cuda(), bias.cuda()
+    out0 = torch.zeros(M, N, device="cuda", dtype=torch.float16)
+    out1 = torch.zeros(M, N, device="cuda", dtype=torch.float16)
+    L.check(lib().magb200_gemm(L.ptr(Ad), L.ptr(Bd), M, N, K, K, K, L.F16, L.F16, 0, 0, L.EPI_GELU_F16, L.ptr(bias_d),
+                               L.ptr(out0), L.ptr(out1), None, N, 1.0, 1, 0, 0, stream()))
+    torch.cuda.synchronize()
+    assert (out0.double().cpu() - gelu).abs().max().item() < 4e-3          # fp16 outputs, |v| up to ~4
+    assert (out1.double().cpu() - dgelu).abs().max().item() < 1.5e-3
+    # without the second output the first is unchanged
+    out0b = torch.zeros_like(out0)
+    L.check(lib().magb200_gemm(L.ptr(Ad), L.ptr(Bd), M, N, K, K, K, L.F16, L.F16, 0, 0, L.EPI_GELU_F16, L.ptr(bias_d),
+                               L.ptr(out0b), None, None, N, 1.0, 1, 0, 0, stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(out0, out0b)
+    # backward epilogue: dU = (dY W) * saved derivative   (B operand MN-major as in the dgrad GEMM)
+    dY = (torch.randn(M, K, generator=g) * 0.5).half()
+    W = (torch.randn(K, N, generator=g) * 0.08).half()          # [K][N]: B[n][k] stored MN-major
+    ref = (dY.double() @ W.double()) * out1.double().cpu()
+    du = torch.zeros(M, N, device="cuda", dtype=torch.float16)
+    dYd, Wd = dY.cuda(), W.cuda()
+    L.check(lib().magb200_gemm(L.ptr(dYd), L.ptr(Wd), M, N, K, K, N, L.F16, L.F16, 0, 1, L.EPI_DGELU_F16, None, L.ptr(du),
+                               None, L.ptr(out1), N, 1.0, 1, 0, 0, stream()))
+    torch.cuda.synchronize()
+    assert (du.double().cpu() - ref).abs().max().item() < 6e-3 * max(1.0, ref.abs().max().item())
+
+
 def test_gemm_rejects_bad_arguments():
     a = torch.zeros(128, 64, device="cuda", dtype=torch.float16)
     o = torch.zeros(128, 128, device="cuda")

@@ -6,7 +6,7 @@ import json,sys
 d=json.loads(sys.stdin.read())
 print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e']['value'], d['eval_forward'])
 "; }
-timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_model.py -x -q 2>&1 | tail -3 | cut -c1-300
+timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_model.py tests/test_gpu_xlnet.py -x -q 2>&1 | tail -3 | cut -c1-300
 if [ ${PIPESTATUS[0]} -ne 0 ]; then echo "tests failed: skipping the benches"; exit 1; fi
 IFS='|' read -ra VS <<< "${VARIANTS:-X=0}"
 i=0
