@@ -97,19 +97,35 @@ struct EpiStage {
   static constexpr int WARP_BYTES = 32 * PITCH;
 };
 
-// global [rows][rowbytes] (pitch gpitch bytes) -> staging, coalesced
+// global [rows][rowbytes] (pitch gpitch bytes) -> staging, coalesced.  Eight row-slices are requested before the first
+// is stored: the one-load-one-store loop this replaces exposed a full global-load latency per slice (32 dependent
+// round trips for an fp32 residual tile -- the dgrad GEMMs that accumulate into the residual gradient took 36 us in
+// the model against 17 us without the auxiliary input).
 __device__ __forceinline__ void stage_in(uint8_t* stg, int pitch, const uint8_t* __restrict__ gsrc, size_t gpitch,
-                                         int rows, int rowbytes, int lane) {
+                                         int rows, int rowbytes, int lane, bool serial = false) {
   const int lpr = rowbytes >> 4;                   // lanes per row (16 B each): 8, 16, 32 or 64
-  if (lpr <= 32) {
-    const int rpi = 32 / lpr;                      // rows per instruction
-    const int lr = lane / lpr, lc = (lane % lpr) << 4;
-    for (int r = lr; r < rows; r += rpi)
-      *reinterpret_cast<uint4*>(stg + r * pitch + lc) = *reinterpret_cast<const uint4*>(gsrc + (size_t)r * gpitch + lc);
-  } else {
-    for (int r = 0; r < rows; ++r)
-      for (int c = lane << 4; c < rowbytes; c += 512)
-        *reinterpret_cast<uint4*>(stg + r * pitch + c) = *reinterpret_cast<const uint4*>(gsrc + (size_t)r * gpitch + c);
+  const int rpi = lpr <= 32 ? 32 / lpr : 1;        // rows per instruction
+  const int lr = lpr <= 32 ? lane / lpr : 0;
+  const int lc0 = lpr <= 32 ? (lane % lpr) << 4 : lane << 4;
+  if (serial) {                                    // measurement mode (dbg 3): the original one-slice-at-a-time loop
+    for (int c = lc0; c < rowbytes; c += 512)
+#pragma unroll 1
+      for (int r = lr; r < rows; r += rpi) {
+        const uint4 v = *reinterpret_cast<const uint4*>(gsrc + (size_t)r * gpitch + c);
+        *reinterpret_cast<uint4*>(stg + r * pitch + c) = v;
+      }
+    return;
+  }
+  for (int c = lc0; c < rowbytes; c += 512) {
+    for (int r = lr; r < rows; r += 8 * rpi) {
+      uint4 v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (r + q * rpi < rows) v[q] = *reinterpret_cast<const uint4*>(gsrc + (size_t)(r + q * rpi) * gpitch + c);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (r + q * rpi < rows) *reinterpret_cast<uint4*>(stg + (r + q * rpi) * pitch + c) = v[q];
+    }
   }
 }
 // staging -> global, coalesced store (or fp32 reduction when `atomic`).  Four row-slices are read from shared
@@ -316,7 +332,7 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& g, uint32_t t
   if (x.live && (x.aux32 || aux16)) {
     const int es = x.aux32 ? 4 : 2;
     stage_in(stg, PITCH, reinterpret_cast<const uint8_t*>(g.aux) + ((size_t)m_base * g.ldo + n0) * es,
-             (size_t)g.ldo * es, rows, ncols * es, lane);
+             (size_t)g.ldo * es, rows, ncols * es, lane, g.dbg == 3);
   }
   __syncwarp();
   // GELU with both outputs (g16 and the pre-activation u16 the backward needs): both are fp16, so the two staged
