@@ -232,7 +232,9 @@ def time_gemm_shapes(torch, L, lib, peaks, T):
         us = e0.elapsed_time(e1) * 1e3 / reps
         flops = 2.0 * M * N * K
         tf = flops / (us * 1e-6) / 1e12
-        out.append({"kernel": "gemm_tcgen05_kernel", "shape": name, "M": M, "N": N, "K": K, "us": round(us, 2),
+        # forward Linears run on the persistent cta_group::2 kernel (profiles/r01_gemm_policy.txt)
+        kern = "gemm2p_tcgen05_kernel<256x%d pair tiles>" % (256 if (N % 256 == 0 and N >= 1024) else 128)
+        out.append({"kernel": kern, "shape": name, "M": M, "N": N, "K": K, "us": round(us, 2),
                     "achieved": round(tf, 1), "frac": round(tf / peaks["tflops_burst"], 4)})
     return out
 
@@ -388,8 +390,8 @@ def run_gpu_arm(args):
     kernels = time_gemm_shapes(torch, L, lib, peaks, BS * SEQ)
     dom = kernels[0]
     roofline = {
-        "bound": "tensor", "kernel": "gemm_tcgen05_kernel<fp16, K-major, 128x128> (FFN-in: M=2400 N=3072 K=768, "
-                                     "bias+GELU epilogue)",
+        "bound": "tensor", "kernel": "gemm2p_tcgen05_kernel<fp16, K-major, persistent cta_group::2, 256x256 pair tiles> "
+                                     "(FFN-in: M=2400 N=3072 K=768, bias + GELU + saved GELU' epilogue)",
         "achieved": dom["achieved"], "peak": peaks["tflops_burst"], "unit": "TFLOP/s", "frac": dom["frac"],
         "traffic": read_profile_traffic(), "peak_source": peaks["source"] + ", burst figure (kernel timed alone)",
         "per_shape": kernels,
