@@ -40,3 +40,28 @@ def grad_unscale(world: int) -> float:
     """Each rank's loss is a MEAN over its local batch (multimodal_driver.py:371-373), so the global-batch
     gradient is the mean of the per-rank gradients: sum-all-reduce, then multiply by 1/world."""
     return 1.0 / float(world)
+
+
+def sparse_rows_allreduce_(table_grad: torch.Tensor, ids: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum over ranks of an embedding-table gradient that is non-zero only in the rows `ids` touched on each rank
+    (word embeddings: <= B*S of 30522 rows, 7 MB instead of 94 MB).  Every rank contributes (ids, rows) with its
+    local row sums split evenly over the duplicates of an id, all-gathers both, and scatter-adds the other ranks'
+    rows into its dense gradient.  Fixed shapes and no host synchronisation (no unique / nonzero), so the whole
+    exchange can be captured in a CUDA graph.  In place; returns `table_grad`.
+
+    table_grad: [vocab, H] fp32 (a view of the flat gradient buffer); ids: this rank's token ids, any shape."""
+    rank, world = world_info(group)
+    if world == 1:
+        return table_grad
+    flat_ids = ids.reshape(-1).to(torch.int64)
+    counts = torch.zeros(table_grad.shape[0], dtype=table_grad.dtype, device=table_grad.device)
+    counts.index_add_(0, flat_ids, torch.ones_like(flat_ids, dtype=table_grad.dtype))
+    rows = table_grad.index_select(0, flat_ids) / counts.index_select(0, flat_ids).unsqueeze(1)
+    all_ids = [torch.empty_like(flat_ids) for _ in range(world)]
+    all_rows = [torch.empty_like(rows) for _ in range(world)]
+    dist.all_gather(all_ids, flat_ids, group=group)
+    dist.all_gather(all_rows, rows, group=group)
+    for r in range(world):
+        if r != rank:
+            table_grad.index_add_(0, all_ids[r], all_rows[r])
+    return table_grad

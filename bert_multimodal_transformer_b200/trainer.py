@@ -25,7 +25,7 @@ import torch
 
 from . import _lib as L
 from .engine import BertEngine
-from .parallel import allreduce_sum_, grad_unscale
+from .parallel import allreduce_sum_, grad_unscale, sparse_rows_allreduce_
 
 
 def linear_schedule(step: int, warmup: int, total: int) -> float:
@@ -100,6 +100,7 @@ class MagBertTrainer:
         self.stream = torch.cuda.Stream(device=dev)
         self.comm_stream = torch.cuda.Stream(device=dev)
         self.overlap = overlap_allreduce
+        self.sparse_embedding_allreduce = os.environ.get("MAGB200_SPARSE_EMB_ALLREDUCE", "0") == "1"
         self.fused_optimizer = os.environ.get("MAGB200_FUSED_OPTIMIZER", "0") == "1"   # measured: no gain (L2-bound GEMMs and the HBM-bound update slow each other), see DESIGN.md
         eng.refresh_operands()
         self.kernel_launches_per_train_step = None
@@ -173,7 +174,15 @@ class MagBertTrainer:
         # what is left: embeddings + the first group of layers, and pooler / MAG / classifier at the end
         lo0, hi0 = groups[-1]
         s, e = eng.layer_grad_range(lo0, hi0)
-        allreduce_sum_(self.grads[:e], self.pg)
+        if self.sparse_embedding_allreduce:
+            # the word-embedding gradient is non-zero in <= B*S of its 30522 rows: exchange (ids, rows) instead of
+            # all-reducing 94 MB (parallel.sparse_rows_allreduce_; opt-in until measured at N = 8)
+            w0, w1 = int(eng.offsets[L.OFF_WORD]), int(eng.offsets[L.OFF_POS])
+            table = self.grads[w0:w0 + eng.vocab * eng.hidden].view(eng.vocab, eng.hidden)
+            sparse_rows_allreduce_(table, i["input_ids"], self.pg)
+            allreduce_sum_(self.grads[w1:e], self.pg)
+        else:
+            allreduce_sum_(self.grads[:e], self.pg)
         allreduce_sum_(self.grads[int(eng.offsets[L.OFF_POOL_W]):], self.pg)
         main.wait_stream(side)
 

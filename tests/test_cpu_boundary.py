@@ -88,6 +88,32 @@ def test_flat_layout_adjacency_alignment_and_decay_flags():
     assert flag("bert.embeddings.word_embeddings.weight") == 1 and flag("classifier.bias") == 0
 
 
+def test_flat_order_is_embeddings_layers_head():
+    """magb200_bert_backward_adamw and the all-reduce buckets of trainer.py slice the flat buffers per encoder layer:
+    they rely on the order [embeddings | layer 0 .. L-1 | pooler, MAG, classifier] with 256-aligned layer starts
+    (model_bert.cu checks the same at run time)."""
+    from bert_multimodal_transformer_b200 import _lib as L
+    from bert_multimodal_transformer_b200.flat import FlatLayout, bert_offsets_table, bert_param_order
+    from oracle import weights
+    layers = 3
+    sd = weights.bert_state_dict(num_layers=layers)
+    lay = FlatLayout([(n, tuple(sd[n].shape)) for n in bert_param_order(layers)])
+    t = bert_offsets_table(lay, layers, 768, 896)
+    starts = [int(t[L.OFF_LAYER0 + L.OFF_PER_LAYER * l + L.LOFF_QKV_W]) for l in range(layers)] + [int(t[L.OFF_POOL_W])]
+    assert all(a < b for a, b in zip(starts, starts[1:])) and all(x % 256 == 0 for x in starts)
+    assert int(t[L.OFF_EMB_LN_B]) < starts[0]                       # every embedding tensor sits in front of layer 0
+    assert starts[-1] < int(t[L.OFF_TOTAL]) == lay.total
+    per_layer = {n for n in lay.entries if ".encoder.layer." in n}
+    for n, (off, _) in lay.entries.items():
+        if n in per_layer:
+            l = int(n.split(".encoder.layer.")[1].split(".")[0])
+            assert starts[l] <= off < starts[l + 1], n              # a layer's tensors are one contiguous slice
+        elif n.startswith("bert.embeddings."):
+            assert off < starts[0], n
+        else:
+            assert off >= starts[-1], n                              # pooler, MAG, classifier
+
+
 def test_linear_schedule_matches_transformers():
     from transformers import get_linear_schedule_with_warmup
     from bert_multimodal_transformer_b200.trainer import linear_schedule

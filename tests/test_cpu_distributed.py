@@ -59,3 +59,31 @@ def test_shard_slice_contract():
     assert shard_slice(128, 3, 8) == slice(48, 64)
     with pytest.raises(ValueError):
         shard_slice(50, 0, 8)
+
+
+def _sparse_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from bert_multimodal_transformer_b200 import parallel
+    g = torch.Generator().manual_seed(100 + rank)
+    vocab, H = 97, 8
+    ids = torch.randint(0, vocab, (3, 11), generator=g)
+    ids[0, :4] = 5                                              # duplicates inside a rank, and id 5 on both ranks
+    contrib = torch.randn(ids.numel(), H, generator=g)
+    dense = torch.zeros(vocab, H).index_add_(0, ids.reshape(-1), contrib)     # what the embedding backward leaves
+    ref = dense.clone()
+    dist.all_reduce(ref)                                        # dense all-reduce = the definition
+    got = parallel.sparse_rows_allreduce_(dense.clone(), ids)
+    ok = torch.allclose(got, ref, atol=1e-5)
+    torch.save({"ok": ok, "err": (got - ref).abs().max().item()}, os.path.join(out_dir, f"sparse{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sparse_embedding_gradient_exchange_equals_dense_allreduce(tmp_path):
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_sparse_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        res = torch.load(os.path.join(str(tmp_path), f"sparse{r}.pt"))
+        assert res["ok"], res
