@@ -6,7 +6,6 @@ FLOP runs in libmagb200.
 """
 from __future__ import annotations
 
-import ctypes
 from ctypes import byref, c_void_p
 from typing import Dict, Optional
 

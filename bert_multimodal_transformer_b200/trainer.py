@@ -16,7 +16,6 @@ from __future__ import annotations
 
 import math
 import os
-from ctypes import byref, c_void_p
 
 import numpy as np
 from typing import Optional
@@ -24,7 +23,7 @@ from typing import Optional
 import torch
 
 from . import _lib as L
-from .engine import BertEngine
+from .engine import BertEngine  # noqa: F401  (re-exported: the trainer drives a BertEngine or an XlnetEngine)
 from .parallel import allreduce_sum_, grad_unscale, sparse_rows_allreduce_
 
 
