@@ -17,14 +17,18 @@ import torch
 
 
 def bert_batch(batch=48, seq=50, visual_dim=47, acoustic_dim=74, vocab=30522, seed=1234,
-               min_len=5, full_length=False):
+               min_len=5, full_length=False, lens=None):
     rng = np.random.Generator(np.random.PCG64(seed))
     ids = np.zeros((batch, seq), np.int64)
     mask = np.zeros((batch, seq), np.int64)
     tt = np.zeros((batch, seq), np.int64)
     vis = rng.standard_normal((batch, seq, visual_dim), dtype=np.float32)
     aco = rng.standard_normal((batch, seq, acoustic_dim), dtype=np.float32)
-    lens = np.full(batch, seq) if full_length else rng.integers(min_len, seq + 1, size=batch)
+    if lens is not None:                       # explicit lengths (edge cases: l = 2 is CLS + SEP only)
+        lens = np.asarray(lens, np.int64)
+        assert lens.shape == (batch,) and lens.min() >= 2 and lens.max() <= seq
+    else:
+        lens = np.full(batch, seq) if full_length else rng.integers(min_len, seq + 1, size=batch)
     for b in range(batch):
         l = int(lens[b])
         ids[b, 0] = 101
@@ -40,14 +44,18 @@ def bert_batch(batch=48, seq=50, visual_dim=47, acoustic_dim=74, vocab=30522, se
 
 
 def xlnet_batch(batch=48, seq=50, visual_dim=47, acoustic_dim=74, vocab=32000, seed=1234,
-                min_len=5, full_length=False):
+                min_len=5, full_length=False, lens=None):
     rng = np.random.Generator(np.random.PCG64(seed))
     ids = np.full((batch, seq), 5, np.int64)
     mask = np.zeros((batch, seq), np.int64)
     tt = np.full((batch, seq), 3, np.int64)
     vis = rng.standard_normal((batch, seq, visual_dim), dtype=np.float32)
     aco = rng.standard_normal((batch, seq, acoustic_dim), dtype=np.float32)
-    lens = np.full(batch, seq) if full_length else rng.integers(min_len, seq + 1, size=batch)
+    if lens is not None:                       # explicit lengths (edge cases: l = 2 is CLS + SEP only)
+        lens = np.asarray(lens, np.int64)
+        assert lens.shape == (batch,) and lens.min() >= 2 and lens.max() <= seq
+    else:
+        lens = np.full(batch, seq) if full_length else rng.integers(min_len, seq + 1, size=batch)
     for b in range(batch):
         l = int(lens[b])  # tokens + SEP + CLS
         pad = seq - l

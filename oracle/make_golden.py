@@ -56,7 +56,8 @@ def make_mag(name, visual_dim, acoustic_dim, beta_shift, zero_rows, wseed, iseed
     print(name, "out mean abs", float(out.abs().mean()))
 
 
-def make_bert(name, batch, visual_dim, acoustic_dim, wseed, iseed, reference_like, with_grads, keep_rows=2):
+def make_bert(name, batch, visual_dim, acoustic_dim, wseed, iseed, reference_like, with_grads, keep_rows=2, seq=50,
+              lens=None):
     _, bert, _ = shim.import_reference(visual_dim, acoustic_dim)
     cfg = shim.bert_config(num_labels=1)
     m = bert.MAG_BertForSequenceClassification(cfg, shim.MultimodalConfig(1.0, 0.5)).eval()
@@ -64,7 +65,7 @@ def make_bert(name, batch, visual_dim, acoustic_dim, wseed, iseed, reference_lik
                                  reference_like=reference_like)
     missing, unexpected = m.load_state_dict(sd, strict=False)
     assert not unexpected and all("position_ids" in k for k in missing), (missing, unexpected)
-    b = gen.bert_batch(batch, 50, visual_dim, acoustic_dim, seed=iseed)
+    b = gen.bert_batch(batch, seq, visual_dim, acoustic_dim, seed=iseed, lens=lens)
     feats = {}
     hooks = [m.bert.MAG.register_forward_hook(lambda _m, _i, o: feats.__setitem__("mag", o.detach())),
              m.bert.embeddings.register_forward_hook(lambda _m, _i, o: feats.__setitem__("emb", o.detach()))]
@@ -79,7 +80,8 @@ def make_bert(name, batch, visual_dim, acoustic_dim, wseed, iseed, reference_lik
     blob = dict(logits=logits.detach().numpy(), loss=np.float64(loss.item()),
                 pooled=enc[1].detach().numpy(), sequence_output=enc[0][:keep_rows].detach().numpy(),
                 mag=feats["mag"][:keep_rows].numpy(), emb=feats["emb"][:keep_rows].numpy(),
-                args=np.array([batch, visual_dim, acoustic_dim, wseed, iseed, int(reference_like)]))
+                args=np.array([batch, visual_dim, acoustic_dim, wseed, iseed, int(reference_like)]),
+                seq=np.int64(seq), lens=np.asarray([] if lens is None else lens, np.int64))
     if with_grads:
         m.zero_grad()
         loss.backward()
@@ -88,14 +90,15 @@ def make_bert(name, batch, visual_dim, acoustic_dim, wseed, iseed, reference_lik
     print(name, "logits", logits.detach().flatten()[:4].tolist(), "loss", loss.item())
 
 
-def make_xlnet(name, batch, visual_dim, acoustic_dim, wseed, iseed, reference_like, with_grads, keep_rows=2):
+def make_xlnet(name, batch, visual_dim, acoustic_dim, wseed, iseed, reference_like, with_grads, keep_rows=2, seq=50,
+               lens=None):
     _, _, xlnet = shim.import_reference(visual_dim, acoustic_dim)
     cfg = shim.xlnet_config(num_labels=1)
     m = xlnet.MAG_XLNetForSequenceClassification(cfg, shim.MultimodalConfig(1.0, 0.5)).eval()
     sd = weights.xlnet_state_dict(visual_dim=visual_dim, acoustic_dim=acoustic_dim, seed=wseed,
                                   reference_like=reference_like)
     m.load_state_dict(sd, strict=True)
-    b = gen.xlnet_batch(batch, 50, visual_dim, acoustic_dim, seed=iseed)
+    b = gen.xlnet_batch(batch, seq, visual_dim, acoustic_dim, seed=iseed, lens=lens)
     feats = {}
     hook = m.transformer.MAG.register_forward_hook(lambda _m, _i, o: feats.__setitem__("mag", o.detach()))
     with torch.set_grad_enabled(with_grads):
@@ -110,7 +113,8 @@ def make_xlnet(name, batch, visual_dim, acoustic_dim, wseed, iseed, reference_li
     blob = dict(logits=logits.detach().numpy(), loss=np.float64(loss.item()),
                 sequence_output=enc[0][:keep_rows].detach().numpy(),
                 mag=feats["mag"].transpose(0, 1)[:keep_rows].numpy(),
-                args=np.array([batch, visual_dim, acoustic_dim, wseed, iseed, int(reference_like)]))
+                args=np.array([batch, visual_dim, acoustic_dim, wseed, iseed, int(reference_like)]),
+                seq=np.int64(seq), lens=np.asarray([] if lens is None else lens, np.int64))
     if with_grads:
         m.zero_grad()
         loss.backward()
@@ -119,9 +123,22 @@ def make_xlnet(name, batch, visual_dim, acoustic_dim, wseed, iseed, reference_li
     print(name, "logits", logits.detach().flatten()[:4].tolist(), "loss", loss.item())
 
 
+def edge_cases():
+    """Shapes the reference's data pipeline can produce at the extremes (multimodal_driver.py:130-205): a sentence
+    with no word tokens (CLS + SEP only: every modality row is zero -> MAG's hm_norm == 0 guard on the whole
+    sequence, XLNet rows that are all padding except two), batch 1, and BERT's maximum sequence length."""
+    make_bert("bert_mosi_minlen_b4", 4, 47, 74, 0, 77, True, True, lens=[2, 3, 50, 2])
+    make_bert("bert_mosi_b1", 1, 47, 74, 0, 78, False, True)
+    make_bert("bert_mosi_s512_b2", 2, 47, 74, 0, 79, False, False, keep_rows=0, seq=512, lens=[512, 300])   # logits/pooled only
+    make_xlnet("xlnet_mosi_minlen_b4", 4, 47, 74, 0, 80, False, True, lens=[2, 3, 50, 2])
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
+    if os.environ.get("MAKE_GOLDEN_ONLY") == "edge":
+        edge_cases()
+        return
     # BASELINE.json configs[0]: MAG(hidden=768, visual=47, acoustic=74), bs=4 seq=50
     make_mag("mag_mosi", 47, 74, 1.0, False, 0, 7, False)
     make_mag("mag_mosi_zero_rows_beta1e-3", 47, 74, 1e-3, True, 0, 8, True)   # alpha<1 branch + hm_norm==0 guard
@@ -135,6 +152,7 @@ def main():
     # configs[3]: MAG-XLNet
     make_xlnet("xlnet_mosi_b8", 8, 47, 74, 0, 1234, False, True)
     make_xlnet("xlnet_mosi_b48", 48, 47, 74, 0, 1234, False, False)
+    edge_cases()
 
 
 if __name__ == "__main__":

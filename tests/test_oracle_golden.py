@@ -86,3 +86,50 @@ def test_xlnet_matches_reference_golden(golden_dir, name, with_grads):
     if with_grads:
         loss.backward()
         _check_grads(g, {k: v.grad for k, v in sd.items() if v.grad is not None})
+
+
+@pytest.mark.parametrize("name,with_grads", [("bert_mosi_minlen_b4", True), ("bert_mosi_b1", True),
+                                             ("bert_mosi_s512_b2", False)])
+def test_bert_edge_cases_match_reference_golden(golden_dir, name, with_grads):
+    """Extremes of the reference's data pipeline: sentences with no word tokens (CLS + SEP only, every modality row
+    zero -> the hm_norm == 0 guard of modeling.py:35-36 on whole sequences), batch 1, and max_position_embeddings."""
+    g = _load(golden_dir, name)
+    B, V, A, wseed, iseed, reflike = [int(x) for x in g["args"]]
+    S, lens = int(g["seq"]), (g["lens"].tolist() or None)
+    sd = weights.bert_state_dict(visual_dim=V, acoustic_dim=A, seed=wseed, reference_like=bool(reflike))
+    if with_grads:
+        sd = {k: v.requires_grad_(True) for k, v in sd.items()}
+    b = gen.bert_batch(B, S, V, A, seed=iseed, lens=lens)
+    want = {}
+    with torch.set_grad_enabled(with_grads):
+        logits = R.mag_bert_forward(sd, b["input_ids"], b["visual"], b["acoustic"], b["attention_mask"],
+                                    b["token_type_ids"], want=want)
+        loss = R.mse_loss(logits, b["labels"])
+    assert np.abs(logits.detach().numpy() - g["logits"]).max() < TOL
+    assert abs(loss.item() - float(g["loss"])) < 1e-5 * max(1.0, abs(float(g["loss"])))
+    assert np.abs(want["pooled"].detach().numpy() - g["pooled"]).max() < TOL
+    if g["mag"].size:
+        k = g["mag"].shape[0]
+        assert np.abs(want["mag"][:k].detach().numpy() - g["mag"]).max() < TOL
+        assert np.abs(want["sequence_output"][:k].detach().numpy() - g["sequence_output"]).max() < 1e-4
+    if with_grads:
+        loss.backward()
+        _check_grads(g, {k: v.grad for k, v in sd.items()})
+
+
+def test_xlnet_edge_case_matches_reference_golden(golden_dir):
+    g = _load(golden_dir, "xlnet_mosi_minlen_b4")
+    B, V, A, wseed, iseed, reflike = [int(x) for x in g["args"]]
+    S, lens = int(g["seq"]), g["lens"].tolist()
+    sd = weights.xlnet_state_dict(visual_dim=V, acoustic_dim=A, seed=wseed, reference_like=bool(reflike))
+    sd = {k: (v.requires_grad_(True) if k != "transformer.mask_emb" else v) for k, v in sd.items()}
+    b = gen.xlnet_batch(B, S, V, A, seed=iseed, lens=lens)
+    want = {}
+    logits = R.mag_xlnet_forward(sd, b["input_ids"], b["visual"], b["acoustic"], b["attention_mask"],
+                                 b["token_type_ids"], want=want)
+    loss = R.mse_loss(logits, b["labels"])
+    assert np.abs(logits.detach().numpy() - g["logits"]).max() < TOL
+    assert abs(loss.item() - float(g["loss"])) < 1e-5
+    assert np.abs(want["mag"][:2].detach().numpy() - g["mag"]).max() < 1e-4
+    loss.backward()
+    _check_grads(g, {k: v.grad for k, v in sd.items() if v.grad is not None})
