@@ -65,6 +65,35 @@ int magb200_mag_fwd(const float* text32, const float* visual, const float* acous
                       reinterpret_cast<__half*>(out16), ST);
 }
 
+int magb200_mag_fwd_exact(const float* text32, const float* visual, const float* acoustic, const float* W_hv,
+                          const float* W_ha, const float* W_v, const float* W_a, const float* bias4,
+                          const float* ln_gamma, const float* ln_beta, float beta_shift, float ln_eps, float p,
+                          uint64_t seed, uint32_t site, int V, int A, int ka, int T, float* split_scratch,
+                          float* gates32, float* out32, void* out16, void* stream) {
+  const int H = 768;
+  MAGB_REQUIRE(ka == H + 128, "mag: ka must be 896");
+  MAGB_REQUIRE(split_scratch != nullptr, "mag_fwd_exact: scratch of 2*(T + 4*768)*ka floats required");
+  float* a_hi = split_scratch;
+  float* a_lo = a_hi + (size_t)T * ka;
+  float* b_hi = a_lo + (size_t)T * ka;
+  float* b_lo = b_hi + (size_t)4 * H * ka;
+  RUN(mag_pack_split(text32, visual, acoustic, W_hv, W_ha, W_v, W_a, V, A, ka, T, a_hi, a_lo, b_hi, b_lo, ST));
+  // gates = A_hi B_hi^T + bias, += A_hi B_lo^T, += A_lo B_hi^T   (three TF32 GEMMs, fp32 accumulation)
+  const float* As[3] = {a_hi, a_hi, a_lo};
+  const float* Bs[3] = {b_hi, b_lo, b_hi};
+  for (int i = 0; i < 3; ++i) {
+    GemmProblem g;
+    g.A = As[i]; g.B = Bs[i]; g.M = T; g.N = 4 * H; g.K = ka; g.lda = ka; g.ldb = ka;
+    g.a_dtype = DT_F32; g.b_dtype = DT_F32; g.epi = EPI_STORE_F32; g.out0 = gates32; g.ldo = 4 * H;
+    g.bias = i == 0 ? bias4 : nullptr;
+    g.aux = i == 0 ? nullptr : gates32;
+    g.n_split = 2 * H; g.k_start_hi = H;
+    RUN(gemm_launch(g, ST));
+  }
+  return mag_tail_fwd(gates32, text32, ln_gamma, ln_beta, beta_shift, ln_eps, p, Seed{seed, nullptr}, site, T, out32,
+                      reinterpret_cast<__half*>(out16), ST);
+}
+
 int magb200_mag_bwd(const float* dout, const float* text32, const void* amag16, const float* gates32,
                     const void* packed16, const float* ln_gamma, float beta_shift, float ln_eps, float p, uint64_t seed,
                     uint32_t site, int V, int A, int ka, int T, float out_scale, void* dgates16, float* dpacked32,

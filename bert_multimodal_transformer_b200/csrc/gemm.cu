@@ -235,7 +235,7 @@ static int gemm_launch_2cta(const GemmProblem& p, int BN, cudaStream_t st, bool 
   const uint32_t fmt = p.a_dtype == DT_BF16 ? 1u : 0u;
   g.idesc = make_idesc(fmt, fmt, p.a_mn, p.b_mn, 256, BN);     // the pair's UMMA: M = 256
   g.trace = persistent ? g_trace : nullptr;
-  g.dbg = (persistent || g_dbg == 3) ? g_dbg : 0;
+  g.dbg = (persistent || g_dbg == 3) ? g_dbg : 0;   // 4: staggered epilogue column groups (persistent kernel)
   g.drop_thresh = 0; g.drop_scale = 1.f; g.drop_site = p.drop_site; g.drop_seed = p.drop_seed.value;
   g.drop_seed_ptr = reinterpret_cast<const unsigned long long*>(p.drop_seed.ptr);
   if (p.drop_p > 0.f) {

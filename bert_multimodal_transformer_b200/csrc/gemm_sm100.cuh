@@ -923,6 +923,9 @@ gemm2p_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                                         nt * BN + cg * WCOLS, WCOLS, lane);
       mbar_wait(&tmem_full[buf], acc_phase);
       tc_fence_after();
+      // experiment (dbg 4): shift the second column group by about half a sub-block so that its arithmetic overlaps
+      // the first group's store phase (the 35 B/clk store path serialises all 8 warps when they store together)
+      if (g.dbg == 4 && cg == 1 && acc_it == 0) __nanosleep(1000);
       if (tr && threadIdx.x == 64 && acc_it < 3) tr[38 + 2 * acc_it] = clock64();
       const int m_base = (2 * mp + (int)crank) * T::BM + q * 32;
 #pragma unroll 1

@@ -61,6 +61,9 @@ int embed_ln_bwd(const EmbedArgs& a, const float* dout, float oscale, float* dwo
                  float* dgamma, float* dbeta, cudaStream_t st);
 int mag_pack_inputs(const float* text, const float* visual, const float* acoustic, int V, int A, int KA, int T,
                     __half* amag, cudaStream_t st);
+int mag_pack_split(const float* text, const float* visual, const float* acoustic, const float* W_hv, const float* W_ha,
+                   const float* W_v, const float* W_a, int V, int A, int KA, int T, float* a_hi, float* a_lo, float* b_hi,
+                   float* b_lo, cudaStream_t st);
 int mag_tail_fwd(const float* G, const float* text32, const float* gamma, const float* beta, float beta_shift, float eps,
                  float p, Seed seed, uint32_t site, int T, float* out32, __half* out16, cudaStream_t st);
 int mag_tail_bwd(const float* dout, const float* G, const float* text32, const float* gamma, float beta_shift, float eps,

@@ -204,6 +204,57 @@ __global__ void __launch_bounds__(128) mag_pack_inputs_kernel(const float* __res
   }
 }
 
+// Split-precision packing for the exact MAG forward: x = hi + lo with hi = x truncated to TF32 (low 13 mantissa bits
+// cleared, so the tensor core reads it exactly) and lo = x - hi (exact in fp32; the tensor core truncates it to 10
+// mantissa bits: relative error 2^-21 of x).  A*B ~= A_hi*B_hi + A_hi*B_lo + A_lo*B_hi, the dropped lo*lo term is 2^-22.
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  lo = x - hi;
+}
+__global__ void __launch_bounds__(128) mag_pack_inputs_split_kernel(const float* __restrict__ text,
+                                                                    const float* __restrict__ visual,
+                                                                    const float* __restrict__ acoustic, int V, int A,
+                                                                    int KA, int T, float* __restrict__ a_hi,
+                                                                    float* __restrict__ a_lo) {
+  const int t = blockIdx.x;
+  if (t >= T) return;
+  for (int c = threadIdx.x; c < KA; c += blockDim.x) {
+    float x = 0.f;
+    if (c < H) x = text[(int64_t)t * H + c];
+    else if (c < H + V) x = visual[(int64_t)t * V + (c - H)];
+    else if (c < H + V + A) x = acoustic[(int64_t)t * A + (c - H - V)];
+    float hi, lo;
+    split_tf32(x, hi, lo);
+    a_hi[(int64_t)t * KA + c] = hi;
+    a_lo[(int64_t)t * KA + c] = lo;
+  }
+}
+__global__ void mag_pack_weights_split_kernel(const float* __restrict__ W_hv, const float* __restrict__ W_ha,
+                                              const float* __restrict__ W_v, const float* __restrict__ W_a, int V, int A,
+                                              int KA, float* __restrict__ b_hi, float* __restrict__ b_lo) {
+  const int row = blockIdx.x;  // 0 .. 4H, same layout as mag_pack_weights_kernel
+  const int blk = row / H, n = row % H;
+  for (int k = threadIdx.x; k < KA; k += blockDim.x) {
+    float x = 0.f;
+    if (k < H) {
+      if (blk == 0) x = W_hv[(int64_t)n * (V + H) + V + k];
+      else if (blk == 1) x = W_ha[(int64_t)n * (A + H) + A + k];
+    } else if (k < H + V) {
+      const int j = k - H;
+      if (blk == 0) x = W_hv[(int64_t)n * (V + H) + j];
+      else if (blk == 2) x = W_v[(int64_t)n * V + j];
+    } else if (k < H + V + A) {
+      const int j = k - H - V;
+      if (blk == 1) x = W_ha[(int64_t)n * (A + H) + j];
+      else if (blk == 3) x = W_a[(int64_t)n * A + j];
+    }
+    float hi, lo;
+    split_tf32(x, hi, lo);
+    b_hi[(int64_t)row * KA + k] = hi;
+    b_lo[(int64_t)row * KA + k] = lo;
+  }
+}
+
 // Backward of embedding LayerNorm+dropout and scatter-add into the three tables.
 // Block (s, z) owns sequence position s: its 8 warps walk the batch rows b = z*8 + warp, z*8 + warp + 8*gridDim.y, ...
 // so the position-table gradient, the LayerNorm parameter gradients and the token-type gradients stay in register
@@ -664,6 +715,18 @@ int mag_pack_inputs(const float* text, const float* visual, const float* acousti
                     __half* amag, cudaStream_t st) {
   MAGB_REQUIRE(V + A <= KA - H, "mag: V+A=%d does not fit KA=%d", V + A, KA);
   mag_pack_inputs_kernel<<<(T + 3) / 4, 128, 0, st>>>(text, visual, acoustic, V, A, KA, T, amag);
+  MAGB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int mag_pack_split(const float* text, const float* visual, const float* acoustic, const float* W_hv, const float* W_ha,
+                   const float* W_v, const float* W_a, int V, int A, int KA, int T, float* a_hi, float* a_lo, float* b_hi,
+                   float* b_lo, cudaStream_t st) {
+  mag_pack_inputs_split_kernel<<<T, 128, 0, st>>>(text, visual, acoustic, V, A, KA, T, a_hi, a_lo);
+  MAGB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  mag_pack_weights_split_kernel<<<4 * H, 128, 0, st>>>(W_hv, W_ha, W_v, W_a, V, A, KA, b_hi, b_lo);
   MAGB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -8,6 +8,8 @@ configs[0]) through magb200_mag_fwd / magb200_mag_bwd.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 from torch import nn
 
@@ -43,10 +45,20 @@ class _MagFunction(torch.autograd.Function):
         out = torch.empty(T, TEXT_DIM, dtype=torch.float32, device=dev)
         p = mod.dropout.p if training else 0.0
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0
-        L.check(lib.magb200_mag_fwd(L.ptr(text), L.ptr(visual), L.ptr(acoustic), L.ptr(packed), L.ptr(bias4),
-                                    L.ptr(gamma), L.ptr(beta), float(mod.beta_shift), float(mod.LayerNorm.eps), p, seed,
-                                    2, mod.visual_dim, mod.acoustic_dim, KA, T, L.ptr(amag), L.ptr(gates), L.ptr(out),
-                                    None, st))
+        if not mod.exact_forward or need_grad:
+            # fp16-operand gate GEMM (the training path; also produces the packed operands backward reads)
+            L.check(lib.magb200_mag_fwd(L.ptr(text), L.ptr(visual), L.ptr(acoustic), L.ptr(packed), L.ptr(bias4),
+                                        L.ptr(gamma), L.ptr(beta), float(mod.beta_shift), float(mod.LayerNorm.eps), p,
+                                        seed, 2, mod.visual_dim, mod.acoustic_dim, KA, T, L.ptr(amag), L.ptr(gates),
+                                        L.ptr(out), None, st))
+        if mod.exact_forward:
+            # split-TF32 gate GEMMs: fp32-accurate gates / output (BASELINE.json configs[0] tolerance 1e-5)
+            scratch = torch.empty(2 * (T + 4 * TEXT_DIM) * KA, dtype=torch.float32, device=dev)
+            L.check(lib.magb200_mag_fwd_exact(L.ptr(text), L.ptr(visual), L.ptr(acoustic), L.ptr(W_hv), L.ptr(W_ha),
+                                              L.ptr(W_v), L.ptr(W_a), L.ptr(bias4), L.ptr(gamma), L.ptr(beta),
+                                              float(mod.beta_shift), float(mod.LayerNorm.eps), p, seed, 2,
+                                              mod.visual_dim, mod.acoustic_dim, KA, T, L.ptr(scratch), L.ptr(gates),
+                                              L.ptr(out), None, st))
         if need_grad:
             ctx.mod, ctx.p, ctx.seed = mod, p, seed
             ctx.save_for_backward(text, amag, gates, packed, gamma)
@@ -101,6 +113,9 @@ class MAG(nn.Module):
         self.LayerNorm = nn.LayerNorm(hidden_size)
         self.dropout = nn.Dropout(dropout_prob)
         self.grad_scale = 1024.0
+        # exact_forward: evaluate the four Linears to fp32 accuracy (three TF32 GEMMs on split operands) instead of
+        # one fp16-operand GEMM; backward is unchanged.  MAGB200_MAG_EXACT=1 turns it on for every MAG instance.
+        self.exact_forward = os.environ.get("MAGB200_MAG_EXACT", "0") == "1"
 
     def forward(self, text_embedding, visual, acoustic):
         if not text_embedding.is_cuda:

@@ -102,6 +102,15 @@ int magb200_mag_fwd(const float* text32, const float* visual, const float* acous
                     const float* bias4, const float* ln_gamma, const float* ln_beta, float beta_shift, float ln_eps,
                     float p, uint64_t seed, uint32_t site, int V, int A, int ka, int T, void* amag16, float* gates32,
                     float* out32, void* out16, void* stream);
+/* The same forward with the four Linears evaluated to fp32 accuracy on the tensor cores: operands split into TF32
+ * hi + lo parts, three kind::tf32 GEMMs (hi*hi + hi*lo + lo*hi) -- for BASELINE.json configs[0]'s 1e-5 tolerance on
+ * MAG.forward (modeling.py:25-51).  Takes the four fp32 weight matrices directly; split_scratch holds
+ * 2 * (T + 4*768) * ka floats.  gates32 is compatible with magb200_mag_bwd (which stays fp16). */
+int magb200_mag_fwd_exact(const float* text32, const float* visual, const float* acoustic, const float* W_hv,
+                          const float* W_ha, const float* W_v, const float* W_a, const float* bias4,
+                          const float* ln_gamma, const float* ln_beta, float beta_shift, float ln_eps, float p,
+                          uint64_t seed, uint32_t site, int V, int A, int ka, int T, float* split_scratch,
+                          float* gates32, float* out32, void* out16, void* stream);
 /* Backward of magb200_mag_fwd from saved amag16 / gates32.  dout is the (loss-scaled) gradient of out32.
  * Writes dtext32 [T][768] (still scaled); accumulates (+=) out_scale * {dW_hv, dW_ha, dW_v, dW_a, dbias4, dgamma, dbeta}.
  * scratch: dgates16 [T][3072] fp16, dpacked32 [3072][ka] fp32. */

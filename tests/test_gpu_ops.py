@@ -264,6 +264,32 @@ def test_mag_op_against_reference_golden(golden_dir, name):
         assert abs(p.grad.norm().item() - ref_norm) <= 2e-2 * ref_norm + 1e-6, k
 
 
+@pytest.mark.parametrize("name", ["mag_mosi", "mag_mosi_zero_rows_beta1e-3", "mag_mosei"])
+def test_mag_exact_forward_meets_the_reference_tolerance(golden_dir, name):
+    """BASELINE.json configs[0] at its own tolerance (1e-5 on MAG.forward): split-TF32 gate GEMMs."""
+    import os
+    import contextlib, io
+    from oracle import inputs as gen, weights
+    from bert_multimodal_transformer_b200.modeling import MAG
+    gld = np.load(os.path.join(golden_dir, name + ".npz"))
+    V, A, wseed, iseed, zero_rows, reflike = [int(x) for x in gld["args"]]
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = MAG(768, float(gld["beta_shift"]), 0.5, visual_dim=V, acoustic_dim=A)
+    m.load_state_dict(weights.mag_state_dict("", 768, V, A, wseed, bool(reflike)))
+    m = m.cuda().eval()
+    m.exact_forward = True
+    text, vis, aco = gen.mag_case(4, 50, 768, V, A, iseed, bool(zero_rows))
+    with torch.no_grad():
+        out = m(text.cuda(), vis.cuda(), aco.cuda())
+    assert np.abs(out.cpu().numpy() - gld["out"]).max() < 1e-5
+    # with gradients enabled the exact output is kept and backward still works
+    text_g = text.cuda().requires_grad_(True)
+    out2 = m(text_g, vis.cuda(), aco.cuda())
+    assert np.abs(out2.detach().cpu().numpy() - gld["out"]).max() < 1e-5
+    (out2 * torch.from_numpy(gld["probe"]).cuda()).sum().backward()
+    assert rel_err(text_g.grad, torch.from_numpy(gld["dtext"])) < 1e-2
+
+
 def test_mag_train_mode_dropout_matches_injected_mask():
     import contextlib, io
     from oracle import inputs as gen, restatement as R, weights
