@@ -86,7 +86,8 @@ SIGNATURES = {
     "magb200_sdpa_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_uint64, c_uint32, c_void_p,
                                  c_void_p, c_void_p]),
     "magb200_sdpa_bwd": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_int, c_float, c_uint64, c_uint32, c_float,
-                                                  c_void_p, c_void_p, c_void_p]),
+                                                  c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "magb200_sdpa_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "magb200_cls_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_uint64, c_uint32, c_void_p,
                                 c_void_p, c_void_p]),
     "magb200_cls_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_uint64, c_uint32, c_float,
@@ -156,6 +157,9 @@ def ptr(t):
     return None if t is None else c_void_p(t.data_ptr())
 
 
-def current_stream():
+def current_stream(device=None):
+    """torch's current stream of `device` (default: the current device).  The native schedules also use the CUDA
+    current device for their per-device state, so callers whose tensors may live on another device wrap the call in
+    `torch.cuda.device(dev)` (the model classes do)."""
     import torch
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)

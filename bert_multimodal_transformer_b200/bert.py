@@ -137,11 +137,14 @@ class _MagBertFunction(torch.autograd.Function):
     def forward(ctx, model, ids, tt, mask, visual, acoustic, training, need_grad, *params):
         eng = model._engine
         B, S = ids.shape
+        # dropout seed of this call: drawn on the HOST from torch's default CPU generator (no device sync; follows
+        # torch.manual_seed like the reference's nn.Dropout layers do)
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0
         dims = eng.dims(B, S, training, seed)
-        ws = eng.workspace(dims, keep=need_grad)
-        logits = torch.empty(B, eng.num_labels, dtype=torch.float32, device=ids.device)
-        eng.forward(dims, ws, ids, tt, mask, visual, acoustic, logits)
+        with torch.cuda.device(eng.flat.device):      # kernels are enqueued on THIS device's current stream
+            ws = eng.workspace(dims, keep=need_grad)
+            logits = torch.empty(B, eng.num_labels, dtype=torch.float32, device=ids.device)
+            eng.forward(dims, ws, ids, tt, mask, visual, acoustic, logits)
         ctx.model, ctx.dims, ctx.ws = model, dims, ws
         ctx.inputs = (ids, tt, mask)
         ctx.nparams = len(params)
@@ -150,11 +153,15 @@ class _MagBertFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dlogits):
-        eng = ctx.model._engine
+        model = ctx.model
+        eng = model._engine
         ids, tt, mask = ctx.inputs
-        grads = torch.zeros_like(eng.flat)
-        dl = (dlogits.to(torch.float32) * eng.grad_scale).contiguous()
-        eng.backward(ctx.dims, ctx.ws, ids, tt, mask, dl, grads)
+        with torch.cuda.device(eng.flat.device):
+            # persistent flat gradient buffer (zeroed, no allocation per step); the per-parameter views returned below
+            # become the .grad tensors, which is what lets optim.AdamW run as one fused launch
+            grads = eng.grad_buffers.take(eng.flat, model._param_list[0])
+            dl = (dlogits.to(torch.float32) * eng.grad_scale).contiguous()
+            eng.backward(ctx.dims, ctx.ws, ids, tt, mask, dl, grads)
         ctx.ws = None
         out = tuple(eng.layout.view(grads, n) for n in eng.order)
         return (None,) * 8 + out
@@ -199,14 +206,8 @@ class MAG_BertForSequenceClassification(nn.Module):
         model = cls(config, multimodal_config)
         if state_dict is None:
             state_dict = _load_checkpoint_state_dict(pretrained_model_name_or_path)
-        if state_dict is not None:
-            own = model.state_dict()
-            renamed = {}
-            for k, v in state_dict.items():
-                k2 = k.replace("gamma", "weight").replace("beta", "bias") if "LayerNorm" in k else k
-                if k2 in own and own[k2].shape == v.shape:
-                    renamed[k2] = v
-            model.load_state_dict(renamed, strict=False)
+        _load_pretrained_into(model, state_dict, pretrained_model_name_or_path,
+                              rename=lambda k: k.replace("gamma", "weight").replace("beta", "bias") if "LayerNorm" in k else k)
         return model
 
     # ------------------------------------------------------------------ plumbing
@@ -253,9 +254,13 @@ class MAG_BertForSequenceClassification(nn.Module):
             raise ValueError(f"visual/acoustic feature dims {vis.shape[-1]}/{aco.shape[-1]} do not match the model "
                              f"({eng.visual_dim}/{eng.acoustic_dim})")
         training = self.training
-        if training or eng.operands_dirty:
-            eng.refresh_operands()
-            eng.operands_dirty = training   # an optimizer step may follow a training forward
+        # fp16 operand mirror: re-derived when flagged dirty.  A training forward flags it for the next call (an external
+        # optimizer may change the fp32 masters in place -- `p.data` updates do not bump version counters, so this
+        # cannot be detected); this package's fused AdamW rewrites the mirror in its kernel and clears the flag
+        if eng.operands_dirty:
+            with torch.cuda.device(dev):
+                eng.refresh_operands()
+        eng.operands_dirty = training    # an optimizer step may follow; optim.AdamW's fused step clears the flag again
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self._param_list)
         params = self._param_list if need_grad else []
         return _MagBertFunction.apply(self, ids, tt, mask, vis, aco, training, need_grad, *params)
@@ -282,8 +287,42 @@ class MAG_BertForSequenceClassification(nn.Module):
         return outputs
 
 
+def _load_pretrained_into(model, state_dict, source, rename=lambda k: k):
+    """Copy a checkpoint into `model` the way transformers' from_pretrained does, and say what happened: no weights
+    file is an error (the reference would fail to resolve the checkpoint too -- fine-tuning silently from a random
+    BERT is the worst outcome); keys missing from the checkpoint (MAG, classifier: expected), unexpected keys and
+    shape mismatches are reported."""
+    import warnings
+    if state_dict is None:
+        raise OSError(f"no weights file (model.safetensors / pytorch_model.bin) found for '{source}': refusing to return "
+                      "a randomly initialised model from from_pretrained(); construct the class from a config instead")
+    own = model.state_dict()
+    loadable, mismatched, unexpected = {}, [], []
+    for k, v in state_dict.items():
+        k2 = rename(k)
+        if k2 not in own:
+            unexpected.append(k)
+        elif tuple(own[k2].shape) != tuple(v.shape):
+            mismatched.append((k2, tuple(v.shape), tuple(own[k2].shape)))
+        else:
+            loadable[k2] = v
+    model.load_state_dict(loadable, strict=False)
+    missing = [k for k in own if k not in loadable]
+    model.pretrained_load_report = {"source": str(source), "loaded": len(loadable), "missing": missing,
+                                    "unexpected": unexpected, "mismatched": mismatched}
+    if mismatched:
+        warnings.warn(f"from_pretrained('{source}'): {len(mismatched)} tensors have a different shape in the checkpoint "
+                      f"and keep their fresh initialisation, e.g. {mismatched[:3]}")
+    if missing:
+        warnings.warn(f"from_pretrained('{source}'): {len(missing)} tensors are not in the checkpoint and are newly "
+                      f"initialised: {missing[:6]}{' ...' if len(missing) > 6 else ''}")
+    if unexpected:
+        warnings.warn(f"from_pretrained('{source}'): {len(unexpected)} checkpoint tensors are not used: {unexpected[:6]}"
+                      f"{' ...' if len(unexpected) > 6 else ''}")
+
+
 def _load_checkpoint_state_dict(name_or_path):
-    """Best-effort local checkpoint lookup (safetensors or torch pickle); None when absent."""
+    """Local checkpoint lookup (safetensors or torch pickle, directory or HF cache entry); None when absent."""
     cands = []
     if os.path.isdir(name_or_path):
         cands = [os.path.join(name_or_path, f) for f in ("model.safetensors", "pytorch_model.bin")]

@@ -262,6 +262,8 @@ int sdpa_fwd(const __half* qkv, const int64_t* mask, int B, int S, int heads, in
   MAGB_REQUIRE(S >= 1 && S <= 512, "sdpa: sequence length %d out of range [1,512]", S);
   // short sequences with an lse buffer: warp-MMA kernel (attention_mma.cu); otherwise the general kernel
   if (S <= 64 && lse != nullptr) return sdpa_fwd_mma(qkv, mask, B, S, heads, p, seed, site, ctx, lse, st);
+  // longer sequences with an lse buffer: non-materialising tensor-core kernel (attention_flash.cu)
+  if (lse != nullptr) return sdpa_fwd_flash(qkv, mask, B, S, heads, p, seed, site, ctx, lse, st);
   if (S <= 64) return launch_fwd<2>(qkv, mask, B, S, heads, p, seed, site, ctx, st);
   if (S <= 128) return launch_fwd<4>(qkv, mask, B, S, heads, p, seed, site, ctx, st);
   if (S <= 256) return launch_fwd<8>(qkv, mask, B, S, heads, p, seed, site, ctx, st);
@@ -289,11 +291,18 @@ static int launch_bwd(const __half* qkv, const __half* dctx, const int64_t* mask
 
 int sdpa_bwd(const __half* qkv, const __half* dctx, const __half* ctx, const float* lse, const int64_t* mask, int B,
              int S, int heads, int head_dim, float p, Seed seed, uint32_t site, float oscale, __half* dqkv, float* dbias,
-             cudaStream_t st) {
+             float* scratch, cudaStream_t st) {
   MAGB_REQUIRE(head_dim == DH, "sdpa: head_dim must be 64");
-  MAGB_REQUIRE(S >= 1 && S <= 128, "sdpa backward: sequence length %d out of range [1,128] (materialises S x S)", S);
+  MAGB_REQUIRE(S >= 1 && S <= 512, "sdpa backward: sequence length %d out of range [1,512]", S);
   if (S <= 64 && lse != nullptr && ctx != nullptr)
     return sdpa_bwd_mma(qkv, dctx, ctx, lse, mask, B, S, heads, p, seed, site, oscale, dqkv, dbias, st);
+  if (lse != nullptr && ctx != nullptr && scratch != nullptr) {
+    int rc = sdpa_bwd_flash(qkv, dctx, ctx, lse, mask, B, S, heads, p, seed, site, scratch, dqkv, st);
+    if (rc) return rc;
+    if (dbias != nullptr) return colsum_f16(dqkv, B * S, 3 * heads * DH, oscale, dbias, st);
+    return 0;
+  }
+  MAGB_REQUIRE(S <= 128, "sdpa backward: S=%d > 128 needs lse, ctx and a workspace (the general kernel materialises S x S)", S);
   int rc = S <= 64 ? launch_bwd<2>(qkv, dctx, mask, B, S, heads, p, seed, site, dqkv, st)
                    : launch_bwd<4>(qkv, dctx, mask, B, S, heads, p, seed, site, dqkv, st);
   if (rc) return rc;

@@ -141,11 +141,15 @@ int magb200_sdpa_fwd(const void* qkv16, const int64_t* mask, int B, int S, int h
 
 int magb200_sdpa_bwd(const void* qkv16, const void* dctx16, const void* ctx16, const float* lse, const int64_t* mask,
                      int B, int S, int heads, int head_dim, float p, uint64_t seed, uint32_t site, float out_scale,
-                     void* dqkv16, float* dbias, void* stream) {
+                     void* dqkv16, float* dbias, void* workspace, size_t workspace_bytes, void* stream) {
+  MAGB_REQUIRE(workspace == nullptr || workspace_bytes >= sdpa_flash_scratch_bytes(B, S, heads),
+               "sdpa_bwd: workspace too small (%zu < %zu)", workspace_bytes, sdpa_flash_scratch_bytes(B, S, heads));
   return sdpa_bwd(reinterpret_cast<const __half*>(qkv16), reinterpret_cast<const __half*>(dctx16),
                   reinterpret_cast<const __half*>(ctx16), lse, mask, B, S, heads, head_dim, p, Seed{seed, nullptr}, site,
-                  out_scale, reinterpret_cast<__half*>(dqkv16), dbias, ST);
+                  out_scale, reinterpret_cast<__half*>(dqkv16), dbias, reinterpret_cast<float*>(workspace), ST);
 }
+
+size_t magb200_sdpa_workspace_bytes(int B, int S, int heads) { return sdpa_flash_scratch_bytes(B, S, heads); }
 
 int magb200_cls_fwd(const float* pre, const float* Wc, const float* bc, int B, int num_labels, float p, uint64_t seed,
                     uint32_t site, float* pooled, float* logits, void* stream) {

@@ -137,6 +137,9 @@ static unsigned long long* g_trace = nullptr;
 static int g_cfg = 0;
 static int g_dbg = 0;
 static int g_policy = 1;   // roles routed to the persistent pair kernel by default: forward Linears (profiles/r01_gemm_policy.txt)
+static int g_streamk = 1;  // atomic-epilogue problems (weight gradients, accumulate-into-residual dgrads, split-K forward
+                           // Linears) go to the persistent pair kernel with stream-K work ranges; MAGB200_STREAMK=0 restores
+                           // the round-1 policy (one-shot pair tiles / whole-tile persistent scheduling)
 void gemm_set_debug(unsigned long long* trace, int cfg) { g_trace = trace; g_cfg = cfg % 100; g_dbg = cfg / 100; }
 
 // ---------------------------------------------------------------------------------------------
@@ -212,7 +215,7 @@ static int launch2p_majors(bool a_mn, bool b_mn, const CUtensorMap& ta, const CU
   return launch2p_variant<true, true, BN, STAGES, NEPI>(ta, tb, g, st);
 }
 
-static int gemm_launch_2cta(const GemmProblem& p, int BN, cudaStream_t st, bool persistent = false) {
+static int gemm_launch_2cta(const GemmProblem& p, int BN, cudaStream_t st, bool persistent = false, bool stream_k = false) {
   const int BK = 64, ATOM = 64, BM = 128;
   CUtensorMap ta, tb;
   int rc;
@@ -245,6 +248,12 @@ static int gemm_launch_2cta(const GemmProblem& p, int BN, cudaStream_t st, bool 
   }
   const int m_pairs = (p.M + 2 * BM - 1) / (2 * BM);
   g.tiles_m = m_pairs; g.tiles_n = (p.N + BN - 1) / BN; g.splits = splits;
+  g.stream_k = 0;
+  if (stream_k) {
+    MAGB_REQUIRE(persistent && p.epi == EPI_ATOMIC_F32, "gemm: stream-K needs the persistent kernel and the atomic epilogue");
+    g.stream_k = 1; g.splits = 1; g.kb_per_split = g.kb_total;
+    MAGB_REQUIRE((long long)g.tiles_m * g.tiles_n * g.kb_total * 128 < (1ll << 31), "gemm: stream-K unit count overflows");
+  }
   if (persistent) {
     if (BN == 256) return launch2p_majors<256, 4, 8>(p.a_mn, p.b_mn, ta, tb, g, st);
     return launch2p_majors<128, 6, 8>(p.a_mn, p.b_mn, ta, tb, g, st);
@@ -262,6 +271,8 @@ int gemm_launch(const GemmProblem& p, cudaStream_t st) {
     if (e && *e && g_cfg == 0 && g_dbg == 0) { const int v = atoi(e); g_cfg = v % 100; g_dbg = v / 100; }
     const char* pol = getenv("MAGB200_GEMM_POLICY");
     if (pol && *pol) g_policy = atoi(pol);
+    const char* sk = getenv("MAGB200_STREAMK");
+    if (sk && *sk) g_streamk = atoi(sk);
   }
   MAGB_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem %dx%dx%d", p.M, p.N, p.K);
   const bool a32 = p.a_dtype == DT_F32, b32 = p.b_dtype == DT_F32;
@@ -285,6 +296,12 @@ int gemm_launch(const GemmProblem& p, cudaStream_t st) {
   // cfg 10: persistent with 256x128 tiles only.
   // default policy (cfg 0): persistent pair kernel for the roles in g_policy (bit 0 forward, bit 1 dgrad, bit 2 wgrad;
   // MAGB200_GEMM_POLICY overrides) -- measured per role in profiles/r01_gemm_policy.txt
+  // stream-K (cfg 0, or forced with cfg 11): every cluster gets the same number of K blocks; 256-column tiles whenever N
+  // allows (fewer operand bytes per flop; tile quantisation no longer matters)
+  if (pair_ok && p.epi == EPI_ATOMIC_F32 && ((g_cfg == 0 && g_streamk) || g_cfg == 11)) {
+    const int bn2 = (p.N % 256 == 0) ? 256 : 128;
+    return gemm_launch_2cta(p, bn2, st, true, true);
+  }
   if (pair_ok && g_cfg == 0 && ((g_policy >> p.role) & 1)) {
     const int bn2 = (p.N % 256 == 0 && p.N >= 1024) ? 256 : 128;
     return gemm_launch_2cta(p, bn2, st, true);

@@ -54,6 +54,8 @@ struct GemmArgs {
   unsigned long long drop_seed;
   const unsigned long long* drop_seed_ptr;
   int tiles_m, tiles_n, splits;   // persistent kernel: pair-tiles along M, tiles along N, K splits
+  int stream_k;                   // persistent kernel, atomic epilogue only: 1 = the (tile, K block) work units are cut
+                                  // into one contiguous, equally long range per cluster (stream-K) instead of whole tiles
   int dbg;   // measurement modes (results are garbage): 1 = MMA issue without waiting for operands,
              // 2 = operand delivery only (no MMA; the consumer releases each stage as soon as it lands)
 };
@@ -545,7 +547,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const float* sb = epi_stage_bias(g, reinterpret_cast<float*>(smem + SM::BIAS_OFFSET) + q * BN, n0, BN, lane);
+    // split-K: the bias rides on the first split only
+    const float* sb = blockIdx.z != 0 ? nullptr
+                                      : epi_stage_bias(g, reinterpret_cast<float*>(smem + SM::BIAS_OFFSET) + q * BN, n0, BN, lane);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     if (tr && threadIdx.x == 64) tr[60] = clock64();
@@ -707,7 +711,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   } else {
     // ------------------------------------------------------------------ epilogue (both CTAs, warps 2..5)
     const int q = warp & 3;
-    const float* sb = epi_stage_bias(g, reinterpret_cast<float*>(smem + SM::BIAS_OFFSET) + q * BN, n0, BN, lane);
+    const float* sb = blockIdx.z != 0 ? nullptr
+                                      : epi_stage_bias(g, reinterpret_cast<float*>(smem + SM::BIAS_OFFSET) + q * BN, n0, BN, lane);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     gemm_epilogue_warp<BN>(g, tmem_base + ((uint32_t)(q * 32) << 16), m0 + q * 32, n0,
@@ -746,6 +751,51 @@ struct Gemm2pSmem {
   static_assert((2 * STAGES + 4) * 8 + 4 <= 256, "barrier area");
 };
 
+// Work of one cluster of the persistent kernel as a sequence of segments (pair tile mp, N tile nt, K blocks
+// [kb_begin, kb_end)).  Static mode: whole tiles (or whole K splits of tiles), cluster c takes c, c + #clusters, ...
+// Stream-K mode: the tiles_m * tiles_n * kb_total (tile, K block) units are numbered tile-major and cluster c takes the
+// contiguous range [c * U / C, (c + 1) * U / C): every cluster runs the same number of K blocks (+-1) whatever the
+// tile count, at the price of a partial-sum epilogue per range boundary -- which is free for the red.add epilogue.
+// At M = 2400 the model's GEMMs have 27 .. 120 pair tiles for 74 clusters, so whole-tile scheduling leaves 20-60 % of
+// the machine idle in the last round; the three warp roles walk the same sequence, so no communication is needed.
+template <typename F>
+__device__ __forceinline__ void for_each_segment(const GemmArgs& g, int cluster_id, int num_clusters, F&& f) {
+  // one loop, one call site of f (the body holds the unrolled issue loops); 32-bit arithmetic (the host checks that
+  // units * clusters fits); results pass through a shuffle so the compiler keeps them in uniform registers -- the TMA
+  // coordinates and loop bounds derived from them feed single-lane issue loops (see warp_idx_uniform)
+  const bool sk = g.stream_k != 0;
+  const uint32_t tiles_mn = (uint32_t)(g.tiles_m * g.tiles_n);
+  const uint32_t units = tiles_mn * (uint32_t)g.kb_total;
+  uint32_t u = sk ? units * (uint32_t)cluster_id / (uint32_t)num_clusters : (uint32_t)cluster_id;
+  const uint32_t u1 = sk ? units * (uint32_t)(cluster_id + 1) / (uint32_t)num_clusters : tiles_mn * (uint32_t)g.splits;
+  while (u < u1) {
+    int mp, nt, kb_begin, kb_end;
+    uint32_t adv;
+    if (sk) {
+      const uint32_t tile = u / (uint32_t)g.kb_total;
+      kb_begin = (int)(u - tile * (uint32_t)g.kb_total);
+      const uint32_t left = u1 - u;
+      kb_end = left < (uint32_t)(g.kb_total - kb_begin) ? kb_begin + (int)left : g.kb_total;
+      mp = (int)(tile % (uint32_t)g.tiles_m);
+      nt = (int)(tile / (uint32_t)g.tiles_m);
+      adv = (uint32_t)(kb_end - kb_begin);
+    } else {
+      mp = (int)(u % (uint32_t)g.tiles_m);
+      const uint32_t r = u / (uint32_t)g.tiles_m;
+      nt = (int)(r % (uint32_t)g.tiles_n);
+      kb_begin = (int)(r / (uint32_t)g.tiles_n) * g.kb_per_split;
+      kb_end = min(kb_begin + g.kb_per_split, g.kb_total);
+      adv = (uint32_t)num_clusters;
+    }
+    mp = __shfl_sync(0xffffffffu, mp, 0);
+    nt = __shfl_sync(0xffffffffu, nt, 0);
+    kb_begin = __shfl_sync(0xffffffffu, kb_begin, 0);
+    kb_end = __shfl_sync(0xffffffffu, kb_end, 0);
+    f(mp, nt, kb_begin, kb_end);
+    u += adv;
+  }
+}
+
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
@@ -775,8 +825,6 @@ gemm2p_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   const uint32_t crank = __shfl_sync(0xffffffffu, cluster_ctarank(), 0);
   const bool leader = crank == 0;
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-  const int tiles_mn = g.tiles_m * g.tiles_n;
-  const int total = tiles_mn * g.splits;
   unsigned long long* tr = g.trace ? g.trace + 64ull * blockIdx.x : nullptr;   // debug: clock64 stamps per CTA
   if (tr && threadIdx.x == 0) tr[0] = clock64();
 
@@ -815,13 +863,9 @@ gemm2p_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = cluster_id; tile < total; tile += num_clusters) {
-        const int mp = tile % g.tiles_m, r = tile / g.tiles_m;
-        const int nt = r % g.tiles_n, z = r / g.tiles_n;
+      for_each_segment(g, cluster_id, num_clusters, [&](int mp, int nt, int kb_begin, int kb_end) {
         const int m0 = (2 * mp + (int)crank) * T::BM;
         const int nb0 = nt * BN + (int)crank * (BN / 2);            // this CTA's half of the B tile
-        const int kb_begin = z * g.kb_per_split;
-        const int kb_end = min(kb_begin + g.kb_per_split, g.kb_total);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (elect_one_sync()) {
@@ -850,7 +894,7 @@ gemm2p_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           ++it;
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-      }
+      });
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only; one lane issues)
@@ -864,10 +908,8 @@ gemm2p_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       uint32_t acc_it = 0;
       int it = 0;
       const uint32_t peer_empty = mapa_shared(&empty_bar[0], 1), peer_tfull = mapa_shared(&tmem_full[0], 1);
-      for (int tile = cluster_id; tile < total; tile += num_clusters, ++acc_it) {
-        const int z = tile / tiles_mn;
-        const int kb_begin = z * g.kb_per_split;
-        const int num_kb = min(kb_begin + g.kb_per_split, g.kb_total) - kb_begin;
+      for_each_segment(g, cluster_id, num_clusters, [&](int, int, int kb_begin, int kb_end) {
+        const int num_kb = kb_end - kb_begin;
         const uint32_t buf = acc_it & 1, acc_phase = (acc_it >> 1) & 1;
         mbar_wait(&tmem_empty[buf], acc_phase ^ 1);      // epilogue warps of both CTAs have drained this buffer
         tc_fence_after();
@@ -905,7 +947,8 @@ gemm2p_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           }
         }
         __syncwarp();
-      }
+        ++acc_it;
+      });
     }
   } else {
     // ------------------------------------------------------------------ epilogue (both CTAs, warps 2 .. 2+NEPI-1)
@@ -915,12 +958,12 @@ gemm2p_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     uint8_t* stg = smem + SM::STG_OFFSET + ew * EpiStage<SM::SUB>::WARP_BYTES;
     const uint32_t empty_remote = mapa_shared(&tmem_empty[0], 0);
     uint32_t acc_it = 0;
-    for (int tile = cluster_id; tile < total; tile += num_clusters, ++acc_it) {
-      const int mp = tile % g.tiles_m, r = tile / g.tiles_m;
-      const int nt = r % g.tiles_n;
+    for_each_segment(g, cluster_id, num_clusters, [&](int mp, int nt, int kb_begin, int) {
       const uint32_t buf = acc_it & 1, acc_phase = (acc_it >> 1) & 1;
-      const float* sbw = epi_stage_bias(g, reinterpret_cast<float*>(smem + SM::BIAS_OFFSET) + ew * WCOLS,
-                                        nt * BN + cg * WCOLS, WCOLS, lane);
+      // the bias belongs to the partial sum that holds the tile's first K block
+      const float* sbw = kb_begin != 0 ? nullptr
+                                       : epi_stage_bias(g, reinterpret_cast<float*>(smem + SM::BIAS_OFFSET) + ew * WCOLS,
+                                                        nt * BN + cg * WCOLS, WCOLS, lane);
       mbar_wait(&tmem_full[buf], acc_phase);
       tc_fence_after();
       // experiment (dbg 4): shift the second column group by about half a sub-block so that its arithmetic overlaps
@@ -939,7 +982,8 @@ gemm2p_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       __syncwarp();
       if (tr && threadIdx.x == 64 && acc_it < 3) tr[39 + 2 * acc_it] = clock64();
       if (lane == 0) mbar_arrive_cluster(empty_remote + buf * 8);
-    }
+      ++acc_it;
+    });
   }
   tc_fence_before();
   __syncthreads();

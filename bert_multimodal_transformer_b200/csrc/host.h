@@ -69,8 +69,11 @@ int mag_tail_fwd(const float* G, const float* text32, const float* gamma, const 
 int mag_tail_bwd(const float* dout, const float* G, const float* text32, const float* gamma, float beta_shift, float eps,
                  float p, Seed seed, uint32_t site, int T, float oscale, __half* dG, float* dtext, float* dgamma,
                  float* dbeta, float* dbias4, cudaStream_t st);
+// zero_after (nullable, normally == pre): rows are rewritten with zeros once read -- `pre` is then a reduction target
+// that the next stream-K GEMM can red.add into without a memset
 int dropout_residual_ln_fwd(const float* pre, const float* res, const float* gamma, const float* beta, float eps, float p,
-                            Seed seed, uint32_t site, int T, float* y32, __half* y16, float* rstd, cudaStream_t st);
+                            Seed seed, uint32_t site, int T, float* y32, __half* y16, float* rstd, cudaStream_t st,
+                            float* zero_after = nullptr);
 int ln_bwd(const float* dy32, const float* y32, const float* gamma, const float* beta, const float* rstd, float p,
            Seed seed, uint32_t site, int T, float oscale, float* dz32, __half* dpre, float* dgamma, float* dbeta,
            float* dbias, cudaStream_t st);
@@ -88,9 +91,16 @@ int dropout_mask(uint8_t* out, int64_t n, float p, Seed seed, uint32_t site, cud
 // receives oscale * column sums of dqkv (the fused q|k|v bias gradient)
 int sdpa_fwd(const __half* qkv, const int64_t* mask, int B, int S, int heads, int head_dim, float p, Seed seed,
              uint32_t site, __half* ctx, float* lse, cudaStream_t st);
+// scratch (nullable): sdpa_flash_scratch_bytes(B, S, heads) bytes, needed by the S > 64 backward (rowsum(dO * O))
 int sdpa_bwd(const __half* qkv, const __half* dctx, const __half* ctx, const float* lse, const int64_t* mask, int B,
              int S, int heads, int head_dim, float p, Seed seed, uint32_t site, float oscale, __half* dqkv, float* dbias,
-             cudaStream_t st);
+             float* scratch, cudaStream_t st);
+// attention_flash.cu: non-materialising kernels for any S (used for S > 64)
+size_t sdpa_flash_scratch_bytes(int B, int S, int heads);
+int sdpa_fwd_flash(const __half* qkv, const int64_t* mask, int B, int S, int heads, float p, Seed seed, uint32_t site,
+                   __half* ctx, float* lse, cudaStream_t st);
+int sdpa_bwd_flash(const __half* qkv, const __half* dctx, const __half* ctx, const float* lse, const int64_t* mask, int B,
+                   int S, int heads, float p, Seed seed, uint32_t site, float* Dq_scratch, __half* dqkv, cudaStream_t st);
 int sdpa_fwd_mma(const __half* qkv, const int64_t* mask, int B, int S, int heads, float p, Seed seed, uint32_t site,
                  __half* ctx, float* lse, cudaStream_t st);
 int sdpa_bwd_mma(const __half* qkv, const __half* dctx, const __half* ctx, const float* lse, const int64_t* mask, int B,

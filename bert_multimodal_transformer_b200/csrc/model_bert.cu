@@ -48,6 +48,7 @@ struct BertWs {
   float* dy32; float* dr32; __half* dpre_f16[2]; __half* dpre_a16[2]; __half* du16[2]; __half* dctx16;
   __half* dqkv16[2]; __half* dG16;
   float* dBmag32; __half* dpool16;
+  float* attD;     // [B][heads][S] rowsum(dO * O) of the layer in flight (attention backward for S > 64)
   size_t bytes;
 };
 
@@ -89,6 +90,7 @@ BertWs carve_ws(const magb200_bert_dims& d, void* base) {
   w.dG16 = c.take<__half>(T * 4 * H);
   w.dBmag32 = c.take<float>((size_t)4 * H * d.ka);
   w.dpool16 = c.take<__half>((size_t)d.batch * H);
+  w.attD = c.take<float>((size_t)d.batch * d.heads * d.seq);
   w.bytes = (c.off + 1023) & ~size_t(1023);
   return w;
 }
@@ -141,6 +143,25 @@ SideCtx g_side[MAGB200_MAX_DEVICES];
     if (_rc) return _rc;     \
   } while (0)
 
+bool streamk_forward() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MAGB200_STREAMK");
+    const char* f = getenv("MAGB200_STREAMK_FWD");
+    v = ((e && e[0] == '0') || (f && f[0] == '0')) ? 0 : 1;
+  }
+  return v != 0;
+}
+
+bool accumulate_dgrad_atomic() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MAGB200_STREAMK");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 // C[M,N] = A[M,K] * W[N,K]^T : forward Linear (both operands K-major, fp16)
 int linear_fwd(const __half* A, int lda, const __half* W, int M, int N, int K, const float* bias, int epi, void* out0,
                void* out1, int ldo, cudaStream_t st, int n_split = 0, int k_start_hi = 0) {
@@ -157,6 +178,12 @@ int linear_dgrad(const __half* dY, int ldy, const __half* W, int ldw, int M, int
   p.A = dY; p.B = W; p.M = M; p.N = Kin; p.K = Nout; p.lda = ldy; p.ldb = ldw; p.b_mn = true;
   p.a_dtype = DT_F16; p.b_dtype = DT_F16; p.epi = epi; p.out0 = out0; p.aux = aux; p.ldo = ldo;
   p.role = 1;
+  // accumulate into the running residual gradient (out0 == aux): a reduction, i.e. the atomic epilogue, which lets
+  // the GEMM run with stream-K work ranges (no auxiliary tile to stage either)
+  if (epi == EPI_STORE_F32 && aux != nullptr && aux == out0 && accumulate_dgrad_atomic()) {
+    p.epi = EPI_ATOMIC_F32;
+    p.aux = nullptr;
+  }
   return gemm_launch(p, st);
 }
 // dW[Nout,Kin] += dY[T,Nout]^T * X[T,Kin] : both operands token-major, read in place (MN-major)
@@ -208,22 +235,29 @@ int bert_forward(const magb200_bert_dims& d, const int64_t* off, const float* P,
   RUN(mag_tail_fwd(w.G32, w.emb32, P + off[MAGB200_OFF_MAG_LN_W], P + off[MAGB200_OFF_MAG_LN_B], d.beta_shift,
                    d.mag_ln_eps, d.p_mag, sd, SITE_MAG, T, w.x32[0], w.x16[0], st));
   // BertEncoder                                                                  bert.py:221-229
+  // The two N = 768 Linears of a layer (attention output, FFN output) have 30 pair tiles for 74 clusters: they run as
+  // stream-K reductions into pre32 (red.add epilogue, bias carried by the partial sum that holds K block 0); the
+  // LayerNorm kernel that consumes pre32 hands it back zeroed.
+  const bool skf = streamk_forward();
+  const int epi768 = skf ? EPI_ATOMIC_F32 : EPI_STORE_F32;
+  float* zero_after = skf ? w.pre32 : nullptr;
+  if (skf) MAGB_CHECK_CUDA(cudaMemsetAsync(w.pre32, 0, (size_t)T * H * sizeof(float), st));
   for (int l = 0; l < d.layers; ++l) {
     const int64_t* o = off + MAGB200_OFF_LAYER0 + (int64_t)l * MAGB200_OFF_PER_LAYER;
     LayerWs& L = w.layer[l];
     RUN(linear_fwd(w.x16[l], H, P16 + o[MAGB200_LOFF_QKV_W], T, 3 * H, H, P + o[MAGB200_LOFF_QKV_B], EPI_STORE_F16,
                    L.qkv16, nullptr, 3 * H, st));
     RUN(sdpa_fwd(L.qkv16, mask, B, S, d.heads, H / d.heads, d.p_attn, sd, site_attn_prob(l), L.ctx16, L.lse, st));
-    RUN(linear_fwd(L.ctx16, H, P16 + o[MAGB200_LOFF_AO_W], T, H, H, P + o[MAGB200_LOFF_AO_B], EPI_STORE_F32, w.pre32,
+    RUN(linear_fwd(L.ctx16, H, P16 + o[MAGB200_LOFF_AO_W], T, H, H, P + o[MAGB200_LOFF_AO_B], epi768, w.pre32,
                    nullptr, H, st));
     RUN(dropout_residual_ln_fwd(w.pre32, w.x32[l], P + o[MAGB200_LOFF_LN1_W], P + o[MAGB200_LOFF_LN1_B], d.ln_eps,
-                                d.p_hidden, sd, site_attn_out(l), T, L.a32, L.a16, L.rstd1, st));
+                                d.p_hidden, sd, site_attn_out(l), T, L.a32, L.a16, L.rstd1, st, zero_after));
     RUN(linear_fwd(L.a16, H, P16 + o[MAGB200_LOFF_F1_W], T, I, H, P + o[MAGB200_LOFF_F1_B], EPI_GELU_F16, L.g16, L.gp16,
                    I, st));
-    RUN(linear_fwd(L.g16, I, P16 + o[MAGB200_LOFF_F2_W], T, H, I, P + o[MAGB200_LOFF_F2_B], EPI_STORE_F32, w.pre32,
+    RUN(linear_fwd(L.g16, I, P16 + o[MAGB200_LOFF_F2_W], T, H, I, P + o[MAGB200_LOFF_F2_B], epi768, w.pre32,
                    nullptr, H, st));
     RUN(dropout_residual_ln_fwd(w.pre32, L.a32, P + o[MAGB200_LOFF_LN2_W], P + o[MAGB200_LOFF_LN2_B], d.ln_eps,
-                                d.p_hidden, sd, site_ffn_out(l), T, w.x32[l + 1], w.x16[l + 1], L.rstd2, st));
+                                d.p_hidden, sd, site_ffn_out(l), T, w.x32[l + 1], w.x16[l + 1], L.rstd2, st, zero_after));
   }
   // BertPooler on the CLS rows (row pitch S*H) + classifier                       bert.py:231, 304-307
   RUN(linear_fwd(w.x16[d.layers], S * H, P16 + off[MAGB200_OFF_POOL_W], B, H, H, P + off[MAGB200_OFF_POOL_B],
@@ -249,7 +283,6 @@ int bert_backward_part(const magb200_bert_dims& d, const int64_t* off, const flo
                        const OptHook* opt) {
   RUN(check_dims(d));
   MAGB_REQUIRE(layer_hi < d.layers && layer_lo >= 0, "bert_backward_part: layer range [%d, %d] out of bounds", layer_lo, layer_hi);
-  MAGB_REQUIRE(d.seq <= 128, "bert_backward: seq=%d > 128 not supported by the attention backward yet", d.seq);
   BertWs w = carve_ws(d, workspace);
   MAGB_REQUIRE(ws_bytes >= w.bytes, "bert_backward: workspace too small (%zu < %zu)", ws_bytes, w.bytes);
   const int B = d.batch, S = d.seq, T = B * S, H = d.hidden, I = d.inter;
@@ -337,7 +370,7 @@ int bert_backward_part(const magb200_bert_dims& d, const int64_t* off, const flo
     RUN(linear_dgrad(dpre_a, H, P16 + o[MAGB200_LOFF_AO_W], H, T, H, H, EPI_STORE_F16, w.dctx16, nullptr, H, st));
     // BertSelfAttention
     RUN(sdpa_bwd(L.qkv16, w.dctx16, L.ctx16, L.lse, mask, B, S, d.heads, H / d.heads, d.p_attn, sd, site_attn_prob(l), us,
-                 dqkv, G + o[MAGB200_LOFF_QKV_B], st));
+                 dqkv, G + o[MAGB200_LOFF_QKV_B], w.attD, st));
     RUN(fork());
     RUN(linear_wgrad(dqkv, 3 * H, w.x16[l], H, T, 3 * H, H, G + o[MAGB200_LOFF_QKV_W], H, 2, us, sst));
     RUN(linear_dgrad(dqkv, 3 * H, P16 + o[MAGB200_LOFF_QKV_W], H, T, H, 3 * H, EPI_STORE_F32, w.dy32, w.dy32, H, st));

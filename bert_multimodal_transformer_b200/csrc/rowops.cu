@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(128) mag_tail_bwd_kernel(
 __global__ void __launch_bounds__(128) dropout_residual_ln_fwd_kernel(
     const float* __restrict__ pre, const float* __restrict__ res, const float* __restrict__ gamma,
     const float* __restrict__ beta, float eps, uint32_t thresh, float scale, Seed seed_in, uint32_t site, int T,
-    float* __restrict__ y32, __half* __restrict__ y16, float* __restrict__ rstd_out) {
+    float* __restrict__ y32, __half* __restrict__ y16, float* __restrict__ rstd_out, float* zero_after) {
   pdl_wait();      // may be launched with the PDL attribute: the predecessor can still be running
   pdl_trigger();   // the next kernel in the stream (a GEMM) may start its private prologue
   const uint64_t seed = seed_in.ptr ? *seed_in.ptr : seed_in.value;
@@ -475,7 +475,25 @@ __global__ void __launch_bounds__(128) dropout_residual_ln_fwd_kernel(
   const int t = blockIdx.x * 4 + warp;
   if (t >= T) return;
   Row z, r;
-  load_row(z, pre + (int64_t)t * H, lane);
+  if (zero_after == nullptr) {
+    load_row(z, pre + (int64_t)t * H, lane);
+  } else {
+    // `pre` is a reduction target (stream-K GEMM, red.add epilogue): hand it back zeroed for the next producer.
+    // zero_after aliases pre, so both accesses are volatile asm with a memory clobber: the compiler must not move
+    // the (restrict-qualified) row load below the store.
+    const float* src = pre + (int64_t)t * H;
+    float* dst = zero_after + (int64_t)t * H;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float4 v;
+      asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                   : "l"(src + col_of(lane, j)) : "memory");
+      z.v[4 * j] = v.x; z.v[4 * j + 1] = v.y; z.v[4 * j + 2] = v.z; z.v[4 * j + 3] = v.w;
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j)
+      asm volatile("st.global.v4.f32 [%0], {%1, %1, %1, %1};" ::"l"(dst + col_of(lane, j)), "f"(0.f) : "memory");
+  }
   row_dropout(z, seed, site, t, lane, thresh, scale);
   load_row(r, res + (int64_t)t * H, lane);
 #pragma unroll
@@ -787,11 +805,11 @@ int mag_tail_bwd(const float* dout, const float* G, const float* text32, const f
 
 int dropout_residual_ln_fwd(const float* pre, const float* res, const float* gamma, const float* beta, float eps, float p,
                             Seed seed, uint32_t site, int T, float* y32, __half* y16, float* rstd,
-                            cudaStream_t st) {
+                            cudaStream_t st, float* zero_after) {
   uint32_t th; float sc;
   drop_params(p, th, sc);
   MAGB_CHECK_CUDA(launch_pdl(dropout_residual_ln_fwd_kernel, dim3((T + 3) / 4), dim3(128), 0, st, pre, res, gamma, beta, eps,
-                             th, sc, seed, site, T, y32, y16, rstd));
+                             th, sc, seed, site, T, y32, y16, rstd, zero_after));
   MAGB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -6,6 +6,7 @@ FLOP runs in libmagb200.
 """
 from __future__ import annotations
 
+import weakref
 from ctypes import byref, c_void_p
 from typing import Dict, Optional
 
@@ -20,6 +21,41 @@ def _require_cuda(t: torch.Tensor, what: str):
         raise L.MagB200Error(
             f"{what} is on {t.device}: bert_multimodal_transformer_b200 only runs on a CUDA (sm_100a) device; "
             "there is no CPU fallback")
+
+
+class _GradBuffers:
+    """Two persistent flat gradient buffers for the autograd entry points (loss.backward() through the class API).
+    The native backward accumulates into a zeroed buffer and returns per-parameter VIEWS of it; autograd adopts those
+    views as `p.grad` (no copy).  A buffer is reused once no parameter's .grad points into it any more (after
+    optimizer.zero_grad(), whether it sets the grads to None or zeroes them in place the other buffer is taken), so a
+    training loop allocates nothing per step."""
+
+    def __init__(self):
+        self.bufs = [None, None]
+        self.last = None
+
+    def take(self, flat: torch.Tensor, probe: torch.nn.Parameter) -> torch.Tensor:
+        n, dev = flat.numel(), flat.device
+        busy = None
+        g = probe.grad
+        if g is not None and g.is_cuda:
+            for i, b in enumerate(self.bufs):
+                if b is not None and b.data_ptr() <= g.data_ptr() < b.data_ptr() + 4 * b.numel():
+                    busy = i
+        i = 1 if busy == 0 else 0
+        b = self.bufs[i]
+        if b is None or b.numel() != n or b.device != dev:
+            b = torch.empty(n, dtype=torch.float32, device=dev)
+            self.bufs[i] = b
+        b.zero_()
+        self.last = b
+        return b
+
+
+def _tag_parameters(engine, named_params, order):
+    ref = weakref.ref(engine)
+    for n in order:
+        named_params[n]._magb200_engine = ref
 
 
 class BertEngine:
@@ -40,8 +76,13 @@ class BertEngine:
         self.flat16: Optional[torch.Tensor] = None     # fp16 mirror + packed MAG gate matrix
         self.offsets = None
         self.operands_dirty = True
+        self.grad_buffers = _GradBuffers()
         self._eval_ws: Dict[tuple, torch.Tensor] = {}
         self._expected_ptrs = None
+
+    @property
+    def last_grad_buffer(self):
+        return self.grad_buffers.last
 
     # ------------------------------------------------------------------ parameters
     def bind(self, named_params: Dict[str, torch.nn.Parameter]):
@@ -65,6 +106,7 @@ class BertEngine:
         self.flat16 = torch.zeros(self.layout.total + packed16_numel(self.hidden, self.ka), dtype=torch.float16,
                                   device=dev)
         self._expected_ptrs = [(named_params[n], self.layout.view(flat, n).data_ptr()) for n in self.order]
+        _tag_parameters(self, named_params, self.order)
         self.operands_dirty = True
         self._eval_ws.clear()
 
@@ -204,8 +246,13 @@ class XlnetEngine:
         self.flat16 = None
         self.offsets = None
         self.operands_dirty = True
+        self.grad_buffers = _GradBuffers()
         self._eval_ws = {}
         self._expected_ptrs = None
+
+    @property
+    def last_grad_buffer(self):
+        return self.grad_buffers.last
 
     def bind(self, named_params):
         from .flat import xlnet_fp16_numel, xlnet_offsets_table
@@ -228,6 +275,7 @@ class XlnetEngine:
         self.flat16 = torch.zeros(xlnet_fp16_numel(self.layout, self.layers, self.hidden, self.ka), dtype=torch.float16,
                                   device=dev)
         self._expected_ptrs = [(named_params[n], self.layout.view(flat, n).data_ptr()) for n in self.order]
+        _tag_parameters(self, named_params, self.order)
         self.operands_dirty = True
         self._eval_ws.clear()
 

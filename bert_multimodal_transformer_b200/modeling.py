@@ -30,8 +30,18 @@ def _dims_from_global_configs():
 
 class _MagFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, mod, training, need_grad, text, visual, acoustic, W_hv, b_hv, W_ha, b_ha, W_v, b_v, W_a, b_a,
-                gamma, beta):
+    def forward(ctx, mod, training, need_grad, *tensors):
+        with torch.cuda.device(tensors[0].device):     # enqueue on the current stream of the tensors' device
+            return _MagFunction._forward(ctx, mod, training, need_grad, *tensors)
+
+    @staticmethod
+    def backward(ctx, dout):
+        with torch.cuda.device(dout.device):
+            return _MagFunction._backward(ctx, dout)
+
+    @staticmethod
+    def _forward(ctx, mod, training, need_grad, text, visual, acoustic, W_hv, b_hv, W_ha, b_ha, W_v, b_v, W_a, b_a,
+                 gamma, beta):
         lib = L.load()
         T = text.shape[0]
         dev = text.device
@@ -66,7 +76,7 @@ class _MagFunction(torch.autograd.Function):
         return out
 
     @staticmethod
-    def backward(ctx, dout):
+    def _backward(ctx, dout):
         lib = L.load()
         mod = ctx.mod
         text, amag, gates, packed, gamma = ctx.saved_tensors

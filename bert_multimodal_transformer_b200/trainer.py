@@ -73,11 +73,17 @@ class MagBertTrainer:
         self.slots_np = [{k: v.numpy() for k, v in sl.items()} for sl in self.slots]
         self.slot = 0
         self.host_in = self.slots[0]
-        # per-step control block (device words the kernels read): dropout seed, lr, Adam step size
-        self.host_seed = [torch.zeros(1, dtype=torch.int64).pin_memory() for _ in range(self.NSLOT)]
+        # per-step control block (device words the kernels read): dropout seed, lr, Adam step size.  It is copied
+        # eagerly (outside the captured graphs) from a ring of pinned host blocks, each guarded by an event recorded
+        # right after its copy: steps can be queued back to back without a later step's controls overwriting a block
+        # an earlier, still queued copy has not read yet
+        self.NCTRL = 8
+        self.host_seed = [torch.zeros(1, dtype=torch.int64).pin_memory() for _ in range(self.NCTRL)]
         self.dev_seed = torch.zeros(1, dtype=torch.int64, device=dev)
-        self.host_hyper = [torch.zeros(2, dtype=torch.float32).pin_memory() for _ in range(self.NSLOT)]
+        self.host_hyper = [torch.zeros(2, dtype=torch.float32).pin_memory() for _ in range(self.NCTRL)]
         self.dev_hyper = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.ctrl_ev = [None] * self.NCTRL
+        self.ctrl_i = 0
         self.logits = torch.zeros(B, Lb, dtype=torch.float32, device=dev)
         self.dlogits = torch.zeros(B, Lb, dtype=torch.float32, device=dev)
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -116,8 +122,6 @@ class MagBertTrainer:
         st = L.current_stream()
         if transfers:
             self._h2d(slot)
-        self.dev_seed.copy_(self.host_seed[slot], non_blocking=True)
-        self.dev_hyper.copy_(self.host_hyper[slot], non_blocking=True)
         i = self.dev_in
         eng.forward(self.train_dims, self.ws, i["input_ids"], i["token_type_ids"], i["attention_mask"], i["visual"],
                     i["acoustic"], self.logits)
@@ -252,16 +256,27 @@ class MagBertTrainer:
         self.stream.synchronize()
 
     def set_step_controls(self):
-        """Host side of the per-step control block: dropout seed, scheduled LR, Adam bias correction."""
+        """Per-step control block: dropout seed, scheduled LR, Adam bias correction -> device words, enqueued on the
+        trainer's stream ahead of the step that reads them."""
         t = self.step_count
         lam = linear_schedule(t, self.warmup_steps, self.total_steps) if self.total_steps > 0 else 1.0
         lr = self.lr * lam
         b1, b2 = self.betas
         k = t + 1
         step_size = lr * math.sqrt(1.0 - b2 ** k) / (1.0 - b1 ** k)
-        self.host_hyper[self.slot][0] = lr
-        self.host_hyper[self.slot][1] = step_size
-        self.host_seed[self.slot][0] = int(torch.randint(0, 2 ** 62, (1,), generator=self._gen).item())
+        r = self.ctrl_i % self.NCTRL
+        self.ctrl_i += 1
+        if self.ctrl_ev[r] is not None:
+            self.ctrl_ev[r].synchronize()          # the copy that last read this pinned block has executed
+        self.host_hyper[r][0] = lr
+        self.host_hyper[r][1] = step_size
+        self.host_seed[r][0] = int(torch.randint(0, 2 ** 62, (1,), generator=self._gen).item())
+        with torch.cuda.stream(self.stream):
+            self.dev_seed.copy_(self.host_seed[r], non_blocking=True)
+            self.dev_hyper.copy_(self.host_hyper[r], non_blocking=True)
+            if self.ctrl_ev[r] is None:
+                self.ctrl_ev[r] = torch.cuda.Event()
+            self.ctrl_ev[r].record()
 
     def launch_train_step(self, transfers=True):
         """Enqueue one training step on the inputs already staged in pinned memory (no host sync).
@@ -271,6 +286,7 @@ class MagBertTrainer:
         slot = self.slot
         if self.use_graph and not transfers:
             if self._train_graph_resident is None:
+                torch.cuda.synchronize(self.dev)   # earlier steps may still be running on self.stream: clone AFTER them
                 saved = (self.eng.flat.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone())
                 self._train_graph_resident = self._capture(lambda: self._train_body(False, slot))
                 self.eng.flat.copy_(saved[0]); self.exp_avg.copy_(saved[1]); self.exp_avg_sq.copy_(saved[2])
@@ -281,6 +297,10 @@ class MagBertTrainer:
                 self._train_graph_resident.replay()
         elif self.use_graph:
             if self._train_graph[slot] is None:
+                # the capture's warm-up run applies an optimizer step that is undone below: the saved copies must be
+                # taken after every step already queued on self.stream has finished (pipelined submit_train_step
+                # reaches this point for slot 1 while step 0 is still running)
+                torch.cuda.synchronize(self.dev)
                 saved = (self.eng.flat.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone())
                 self._train_graph[slot] = self._capture(lambda: self._train_body(True, slot))
                 # the warm-up run inside _capture applied one optimizer step: undo it

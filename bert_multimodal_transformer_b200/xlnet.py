@@ -138,11 +138,12 @@ class _MagXlnetFunction(torch.autograd.Function):
     def forward(ctx, model, ids, tt, mask, visual, acoustic, training, need_grad, *params):
         eng = model._engine
         B, S = ids.shape
-        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0    # host draw, no device sync
         dims = eng.dims(B, S, training, seed)
-        ws = eng.workspace(dims, keep=need_grad)
-        logits = torch.empty(B, eng.num_labels, dtype=torch.float32, device=ids.device)
-        eng.forward(dims, ws, ids, tt, mask, visual, acoustic, logits)
+        with torch.cuda.device(eng.flat.device):
+            ws = eng.workspace(dims, keep=need_grad)
+            logits = torch.empty(B, eng.num_labels, dtype=torch.float32, device=ids.device)
+            eng.forward(dims, ws, ids, tt, mask, visual, acoustic, logits)
         ctx.model, ctx.dims, ctx.ws = model, dims, ws
         ctx.inputs = (ids, tt, mask)
         model._last = (dims, ws)
@@ -150,11 +151,13 @@ class _MagXlnetFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dlogits):
-        eng = ctx.model._engine
+        model = ctx.model
+        eng = model._engine
         ids, tt, mask = ctx.inputs
-        grads = torch.zeros_like(eng.flat)
-        dl = (dlogits.to(torch.float32) * eng.grad_scale).contiguous()
-        eng.backward(ctx.dims, ctx.ws, ids, tt, mask, dl, grads)
+        with torch.cuda.device(eng.flat.device):
+            grads = eng.grad_buffers.take(eng.flat, model._param_list[0])    # persistent, zeroed (engine._GradBuffers)
+            dl = (dlogits.to(torch.float32) * eng.grad_scale).contiguous()
+            eng.backward(ctx.dims, ctx.ws, ids, tt, mask, dl, grads)
         ctx.ws = None
         return (None,) * 8 + tuple(eng.layout.view(grads, n) for n in eng.order)
 
@@ -190,7 +193,7 @@ class MAG_XLNetForSequenceClassification(nn.Module):
                         config=None, state_dict=None, **kwargs):
         """multimodal_driver.py:321-323.  Offline resolution as in bert.MAG_BertForSequenceClassification."""
         from transformers import XLNetConfig
-        from .bert import _load_checkpoint_state_dict
+        from .bert import _load_checkpoint_state_dict, _load_pretrained_into
         if multimodal_config is None and model_args:
             multimodal_config = model_args[0]
         if config is None:
@@ -199,10 +202,7 @@ class MAG_XLNetForSequenceClassification(nn.Module):
         model = cls(config, multimodal_config)
         if state_dict is None:
             state_dict = _load_checkpoint_state_dict(pretrained_model_name_or_path)
-        if state_dict is not None:
-            own = model.state_dict()
-            model.load_state_dict({k: v for k, v in state_dict.items() if k in own and own[k].shape == v.shape},
-                                  strict=False)
+        _load_pretrained_into(model, state_dict, pretrained_model_name_or_path)
         return model
 
     def _ensure_bound(self):
@@ -252,9 +252,10 @@ class MAG_XLNetForSequenceClassification(nn.Module):
             raise ValueError(f"visual/acoustic feature dims {vis.shape[-1]}/{aco.shape[-1]} do not match the model "
                              f"({eng.visual_dim}/{eng.acoustic_dim})")
         training = self.training
-        if training or eng.operands_dirty:
-            eng.refresh_operands()
-            eng.operands_dirty = training
+        if eng.operands_dirty:                                             # see bert.MAG_BertForSequenceClassification._run
+            with torch.cuda.device(dev):
+                eng.refresh_operands()
+        eng.operands_dirty = training
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self._param_list)
         params = self._param_list if need_grad else []
         return _MagXlnetFunction.apply(self, ids, tt, mask, vis, aco, training, need_grad, *params)

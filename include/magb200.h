@@ -136,14 +136,17 @@ int magb200_colsum_f16(const void* in_f16, int T, int N, float out_scale, float*
  *   ctx = dropout(softmax(q k^T / 8 + (1 - mask) * -10000)) v  per (batch, head)
  * qkv16 [B*S][3*heads*64] fp16 (q | k | v), mask [B][S] int64 (1 = attend) or NULL, ctx16 [B*S][heads*64]
  * lse (optional, [B][heads][S] fp32): forward writes max + log-sum-exp of every score row; with lse and ctx16
- * present and S <= 64 the warp-MMA kernels run (probabilities never leave registers), otherwise the general
- * kernels (forward S <= 512, backward S <= 128).  dbias (optional) += out_scale * column sums of dqkv, i.e. the
- * gradient of the fused query|key|value bias. */
+ * present the tensor-core kernels run and probabilities never leave registers: one tile per (batch, head) for
+ * S <= 64, a flash-style loop over 64-key blocks with online softmax for longer sequences (S <= 512, the limit
+ * of BERT's position table); the backward of the latter needs `workspace` (magb200_sdpa_workspace_bytes: one fp32
+ * per (batch, head, query)).  Without lse the general CUDA-core kernels run (forward S <= 512, backward S <= 128).
+ * dbias (optional) += out_scale * column sums of dqkv, i.e. the gradient of the fused query|key|value bias. */
 int magb200_sdpa_fwd(const void* qkv16, const int64_t* mask, int B, int S, int heads, int head_dim, float p,
                      uint64_t seed, uint32_t site, void* ctx16, float* lse, void* stream);
 int magb200_sdpa_bwd(const void* qkv16, const void* dctx16, const void* ctx16, const float* lse, const int64_t* mask,
                      int B, int S, int heads, int head_dim, float p, uint64_t seed, uint32_t site, float out_scale,
-                     void* dqkv16, float* dbias, void* stream);
+                     void* dqkv16, float* dbias, void* workspace, size_t workspace_bytes, void* stream);
+size_t magb200_sdpa_workspace_bytes(int B, int S, int heads);
 
 /* BertPooler tanh + dropout + classifier (bert.py:231, 304-307): pre [B][768] = pooler dense output */
 int magb200_cls_fwd(const float* pre, const float* Wc, const float* bc, int B, int num_labels, float p, uint64_t seed,

@@ -36,6 +36,11 @@ def _g(seed=0):
     (2400, 768, 768, 0, 0, "f32"), (2400, 2304, 768, 0, 0, "f16"), (304, 256, 320, 1, 0, "f32"),
     (300, 256, 320, 0, 1, "f32"), (768, 768, 2400, 1, 1, "atomic"), (48, 768, 768, 0, 0, "f32"),
     (129, 32, 8, 0, 0, "f32"),
+    # reductions scheduled with stream-K work ranges (persistent pair kernel): the model's weight-gradient,
+    # accumulate-into-residual dgrad and N = 768 forward shapes, a shape with fewer tiles than clusters, ragged M / K
+    (3072, 768, 2400, 1, 1, "atomic"), (2304, 768, 2400, 1, 1, "atomic"), (2400, 768, 3072, 0, 1, "atomic"),
+    (2400, 768, 3072, 0, 0, "atomic"), (2400, 768, 768, 0, 0, "atomic"), (300, 256, 200, 0, 0, "atomic"),
+    (100, 96, 64, 0, 0, "atomic"),
 ])
 def test_gemm(M, N, K, a_mn, b_mn, epi):
     g = _g(1)
@@ -53,7 +58,7 @@ def test_gemm(M, N, K, a_mn, b_mn, epi):
         out, code = torch.zeros(M, N, device="cuda", dtype=torch.float16), L.EPI_STORE_F16
     else:
         out, code, splits = torch.ones(M, N, device="cuda"), L.EPI_ATOMIC_F32, 4
-        ref = ref + 1 + (splits - 1) * bias.double()   # the bias is added once per K split
+        ref = ref + 1                                  # accumulates into the output; the bias is added once
     L.check(lib().magb200_gemm(L.ptr(Ad), L.ptr(Bd), M, N, K, Ad.shape[1], Bd.shape[1], L.F16, L.F16, a_mn, b_mn, code,
                                L.ptr(bias_d), L.ptr(out), None, None, N, 1.0, splits, 0, 0, stream()))
     torch.cuda.synchronize()
@@ -190,7 +195,10 @@ def test_dropout_residual_ln_fwd_bwd(p):
 
 
 @pytest.mark.parametrize("S,p,mma", [(50, 0.0, True), (50, 0.1, True), (17, 0.0, True), (64, 0.1, True), (1, 0.0, True),
-                                     (50, 0.1, False), (128, 0.0, False)])
+                                     (50, 0.1, False), (128, 0.0, False),
+                                     # S > 64 with lse: the flash-style kernels (attention_flash.cu)
+                                     (65, 0.0, True), (100, 0.1, True), (128, 0.1, True), (200, 0.0, True),
+                                     (333, 0.1, True), (512, 0.1, True)])
 def test_sdpa_fwd_bwd(S, p, mma):
     g = _g(4)
     B, heads, d = 3, 12, 64
@@ -221,8 +229,12 @@ def test_sdpa_fwd_bwd(S, p, mma):
         assert (lse.cpu() - lse_ref).abs().max().item() < 2e-3
     dqkv = torch.zeros(B * S, 3 * heads * d, device="cuda", dtype=torch.float16)
     dbias = torch.zeros(3 * heads * d, device="cuda")
+    ws_bytes = lib().magb200_sdpa_workspace_bytes(B, S, heads)
+    assert ws_bytes == B * heads * S * 4
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda") if mma else None
     L.check(lib().magb200_sdpa_bwd(L.ptr(qkv_d), L.ptr(dctx_d), L.ptr(ctx) if mma else None, L.ptr(lse), L.ptr(mask_d), B,
-                                   S, heads, d, p, seed, site, 0.5, L.ptr(dqkv), L.ptr(dbias), stream()))
+                                   S, heads, d, p, seed, site, 0.5, L.ptr(dqkv), L.ptr(dbias), L.ptr(ws),
+                                   ws_bytes if mma else 0, stream()))
     assert rel_err(dqkv.float(), dqkv_ref) < 6e-3
     assert rel_err(dbias, 0.5 * dqkv_ref.sum(0)) < 1e-2
 
