@@ -285,6 +285,10 @@ int gemm_launch(const GemmProblem& p, cudaStream_t st) {
   const int BN = (g_cfg == 3 || g_cfg == 4) ? 256 : 128;
   MAGB_REQUIRE(p.N % 32 == 0, "gemm: N=%d must be a multiple of 32", p.N);
   MAGB_REQUIRE(p.ldo % 8 == 0, "gemm: ldo=%d must be a multiple of 8", p.ldo);
+  // the staged red.add epilogue hands whole 16-byte row pieces to lanes: a tile's column count must be 32, 64, 128 or 256
+  // (with other widths lanes would repeat pieces, harmless for stores but a double count for reductions)
+  MAGB_REQUIRE(p.epi != EPI_ATOMIC_F32 || p.N % 128 == 0 || p.N == 32 || p.N == 64,
+               "gemm: the atomic epilogue needs N = 32, 64 or a multiple of 128 (got %d)", p.N);
   // 2-CTA (cta_group::2) pair tiles.  Measured on B200 (profiles/r01_gemm_modes.txt, r01_gemm_tile_sweep.txt):
   // the 1-CTA 128x128 SS-mode main loop is shared-memory-bandwidth bound (UMMA operand reads 128 B/clk + TMA fill
   // 128 B/clk against 128 B/clk of SMEM), the pair tile halves the per-SM B traffic.  At these problem sizes

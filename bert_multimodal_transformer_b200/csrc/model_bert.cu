@@ -41,7 +41,7 @@ struct BertWs {
   float* x32[MAGB200_MAX_LAYERS + 1];
   __half* x16[MAGB200_MAX_LAYERS + 1];
   LayerWs layer[MAGB200_MAX_LAYERS];
-  float* pre32; float* poolpre32; float* pooled32;
+  float* pre32; float* pre32b; float* pre32c; float* poolpre32; float* pooled32;
   // backward scratch
   // The fp16 gradient tensors the weight-gradient GEMMs consume exist twice (layer parity): those GEMMs run on a
   // side stream and may still be reading layer l+1's copy while the main chain produces layer l's.
@@ -76,6 +76,8 @@ BertWs carve_ws(const magb200_bert_dims& d, void* base) {
     L.lse = c.take<float>((size_t)d.batch * d.heads * d.seq);
   }
   w.pre32 = c.take<float>(T * H);
+  w.pre32b = c.take<float>(T * H);
+  w.pre32c = c.take<float>(T * H);
   w.poolpre32 = c.take<float>((size_t)d.batch * H);
   w.pooled32 = c.take<float>((size_t)d.batch * H);
   w.dy32 = c.take<float>(T * H);
@@ -143,14 +145,14 @@ SideCtx g_side[MAGB200_MAX_DEVICES];
     if (_rc) return _rc;     \
   } while (0)
 
-bool streamk_forward() {
+int streamk_forward() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("MAGB200_STREAMK");
     const char* f = getenv("MAGB200_STREAMK_FWD");
-    v = ((e && e[0] == '0') || (f && f[0] == '0')) ? 0 : 1;
+    v = (e && e[0] == '0') ? 0 : (f && *f ? atoi(f) : 0);
   }
-  return v != 0;
+  return v;
 }
 
 bool accumulate_dgrad_atomic() {
@@ -235,29 +237,33 @@ int bert_forward(const magb200_bert_dims& d, const int64_t* off, const float* P,
   RUN(mag_tail_fwd(w.G32, w.emb32, P + off[MAGB200_OFF_MAG_LN_W], P + off[MAGB200_OFF_MAG_LN_B], d.beta_shift,
                    d.mag_ln_eps, d.p_mag, sd, SITE_MAG, T, w.x32[0], w.x16[0], st));
   // BertEncoder                                                                  bert.py:221-229
-  // The two N = 768 Linears of a layer (attention output, FFN output) have 30 pair tiles for 74 clusters: they run as
-  // stream-K reductions into pre32 (red.add epilogue, bias carried by the partial sum that holds K block 0); the
-  // LayerNorm kernel that consumes pre32 hands it back zeroed.
-  const bool skf = streamk_forward();
-  const int epi768 = skf ? EPI_ATOMIC_F32 : EPI_STORE_F32;
-  float* zero_after = skf ? w.pre32 : nullptr;
-  if (skf) MAGB_CHECK_CUDA(cudaMemsetAsync(w.pre32, 0, (size_t)T * H * sizeof(float), st));
+  // The FFN-output Linear (N = 768, K = 3072) has 30 pair tiles of 48 K blocks for 74 clusters: it can run as a stream-K
+  // reduction into a zeroed buffer (red.add epilogue, bias carried by the partial sum that holds K block 0), which the
+  // LayerNorm kernel that consumes it hands back zeroed.  MAGB200_STREAMK_FWD: 0 = off, 1 = FFN-out, 2 = attention
+  // output too (K = 768: 5 K blocks per cluster against a full-tile reduction epilogue -- measured slower).
+  const int skf = streamk_forward();
+  const int epi_ffn = skf >= 1 ? EPI_ATOMIC_F32 : EPI_STORE_F32, epi_ao = skf >= 2 ? EPI_ATOMIC_F32 : EPI_STORE_F32;
+  float* pre_ffn = skf >= 1 ? w.pre32b : w.pre32;       // reduction targets are dedicated, always-zero buffers
+  float* pre_ao = skf >= 2 ? w.pre32c : w.pre32;
+  if (skf >= 1) MAGB_CHECK_CUDA(cudaMemsetAsync(w.pre32b, 0, (size_t)T * H * sizeof(float), st));
+  if (skf >= 2) MAGB_CHECK_CUDA(cudaMemsetAsync(w.pre32c, 0, (size_t)T * H * sizeof(float), st));
   for (int l = 0; l < d.layers; ++l) {
     const int64_t* o = off + MAGB200_OFF_LAYER0 + (int64_t)l * MAGB200_OFF_PER_LAYER;
     LayerWs& L = w.layer[l];
     RUN(linear_fwd(w.x16[l], H, P16 + o[MAGB200_LOFF_QKV_W], T, 3 * H, H, P + o[MAGB200_LOFF_QKV_B], EPI_STORE_F16,
                    L.qkv16, nullptr, 3 * H, st));
     RUN(sdpa_fwd(L.qkv16, mask, B, S, d.heads, H / d.heads, d.p_attn, sd, site_attn_prob(l), L.ctx16, L.lse, st));
-    RUN(linear_fwd(L.ctx16, H, P16 + o[MAGB200_LOFF_AO_W], T, H, H, P + o[MAGB200_LOFF_AO_B], epi768, w.pre32,
+    RUN(linear_fwd(L.ctx16, H, P16 + o[MAGB200_LOFF_AO_W], T, H, H, P + o[MAGB200_LOFF_AO_B], epi_ao, pre_ao,
                    nullptr, H, st));
-    RUN(dropout_residual_ln_fwd(w.pre32, w.x32[l], P + o[MAGB200_LOFF_LN1_W], P + o[MAGB200_LOFF_LN1_B], d.ln_eps,
-                                d.p_hidden, sd, site_attn_out(l), T, L.a32, L.a16, L.rstd1, st, zero_after));
+    RUN(dropout_residual_ln_fwd(pre_ao, w.x32[l], P + o[MAGB200_LOFF_LN1_W], P + o[MAGB200_LOFF_LN1_B], d.ln_eps,
+                                d.p_hidden, sd, site_attn_out(l), T, L.a32, L.a16, L.rstd1, st, skf >= 2 ? pre_ao : nullptr));
     RUN(linear_fwd(L.a16, H, P16 + o[MAGB200_LOFF_F1_W], T, I, H, P + o[MAGB200_LOFF_F1_B], EPI_GELU_F16, L.g16, L.gp16,
                    I, st));
-    RUN(linear_fwd(L.g16, I, P16 + o[MAGB200_LOFF_F2_W], T, H, I, P + o[MAGB200_LOFF_F2_B], epi768, w.pre32,
+    RUN(linear_fwd(L.g16, I, P16 + o[MAGB200_LOFF_F2_W], T, H, I, P + o[MAGB200_LOFF_F2_B], epi_ffn, pre_ffn,
                    nullptr, H, st));
-    RUN(dropout_residual_ln_fwd(w.pre32, L.a32, P + o[MAGB200_LOFF_LN2_W], P + o[MAGB200_LOFF_LN2_B], d.ln_eps,
-                                d.p_hidden, sd, site_ffn_out(l), T, w.x32[l + 1], w.x16[l + 1], L.rstd2, st, zero_after));
+    RUN(dropout_residual_ln_fwd(pre_ffn, L.a32, P + o[MAGB200_LOFF_LN2_W], P + o[MAGB200_LOFF_LN2_B], d.ln_eps,
+                                d.p_hidden, sd, site_ffn_out(l), T, w.x32[l + 1], w.x16[l + 1], L.rstd2, st,
+                                skf >= 1 ? pre_ffn : nullptr));
   }
   // BertPooler on the CLS rows (row pitch S*H) + classifier                       bert.py:231, 304-307
   RUN(linear_fwd(w.x16[d.layers], S * H, P16 + off[MAGB200_OFF_POOL_W], B, H, H, P + off[MAGB200_OFF_POOL_B],

@@ -14,6 +14,7 @@ its own slice of the batch; the only collective is the gradient all-reduce over 
 """
 from __future__ import annotations
 
+import ctypes
 import math
 import os
 
@@ -105,7 +106,9 @@ class MagBertTrainer:
         self.stream = torch.cuda.Stream(device=dev)
         self.comm_stream = torch.cuda.Stream(device=dev)
         self.overlap = overlap_allreduce
-        self.sparse_embedding_allreduce = os.environ.get("MAGB200_SPARSE_EMB_ALLREDUCE", "0") == "1"
+        self.sparse_embedding_allreduce = os.environ.get("MAGB200_SPARSE_EMB_ALLREDUCE", "1") == "1" and \
+            hasattr(eng, "vocab") and hasattr(eng, "backward_part")
+        self.bucket_adamw = os.environ.get("MAGB200_BUCKET_ADAMW", "1") == "1"
         self.fused_optimizer = os.environ.get("MAGB200_FUSED_OPTIMIZER", "0") == "1"   # measured: no gain (L2-bound GEMMs and the HBM-bound update slow each other), see DESIGN.md
         eng.refresh_operands()
         self.kernel_launches_per_train_step = None
@@ -138,6 +141,11 @@ class MagBertTrainer:
             return
         if self.world > 1 and self.overlap and hasattr(eng, "backward_part"):
             self._backward_overlapped(i)
+            if self.bucket_adamw:            # every slice was updated behind its all-reduce
+                eng.after_optimizer_step()
+                if transfers:
+                    self.host_loss[slot].copy_(self.loss, non_blocking=True)
+                return
         else:
             eng.backward(self.train_dims, self.ws, i["input_ids"], i["token_type_ids"], i["attention_mask"], self.dlogits,
                          self.grads)
@@ -151,42 +159,67 @@ class MagBertTrainer:
         if transfers:
             self.host_loss[slot].copy_(self.loss, non_blocking=True)
 
+    def _adamw_range(self, s0, s1, stream_handle):
+        """AdamW over elements [s0, s1) of the flat buffers (256-aligned slice) on the given stream."""
+        if s1 <= s0:
+            return
+        eng, lib = self.eng, L.load()
+        assert s0 % 256 == 0 and s1 % 256 == 0, (s0, s1)
+        f = lambda t, es: ctypes.c_void_p(t.data_ptr() + es * s0)   # noqa: E731
+        L.check(lib.magb200_adamw_step(f(eng.flat, 4), f(self.grads, 4), f(self.exp_avg, 4), f(self.exp_avg_sq, 4),
+                                       f(eng.flat16, 2), ctypes.c_void_p(self.decay.data_ptr() + s0 // 256), s1 - s0, self.lr,
+                                       self.betas[0], self.betas[1], self.eps, self.wd, 1, grad_unscale(self.world), 1,
+                                       L.ptr(self.dev_hyper), stream_handle))
+
     def _backward_overlapped(self, i):
-        """Backward in pieces (MAGB200_ALLREDUCE_GROUPS layer groups, default 6); the gradient range of each finished group of layers is all-reduced on a side
-        stream while the next piece computes (bucketed overlap).  The order of the flat buffer
-        is [embeddings | layer 0 .. L-1 | pooler, MAG, classifier], so a group of layers is one contiguous slice."""
+        """Data-parallel backward.  The order of the flat buffers is
+        [embeddings | layer 0 .. L-1 | pooler, MAG, classifier], so a group of layers is one contiguous slice.
+
+        Backward runs in pieces (MAGB200_ALLREDUCE_GROUPS layer groups, default 12 = one per layer); as soon as a piece
+        has finished, its gradient slice is all-reduced on the communication stream AND, right behind it on the same
+        stream, updated by AdamW (MAGB200_BUCKET_ADAMW=0 turns that off) while the main stream continues with the next
+        piece: the NVLink transfer and the HBM-bound update both hide under the tensor-core-bound backward of the layers
+        below.  What is left when backward ends is only the bottom piece: the last layer group, the word-embedding
+        gradient -- exchanged as (token ids, rows) instead of a dense 94 MB all-reduce, it is non-zero in at most B*S
+        of its 30522 rows (MAGB200_SPARSE_EMB_ALLREDUCE=0 for the dense form) -- the small position / type / LayerNorm
+        tensors, and pooler / MAG / classifier."""
         eng = self.eng
         main = torch.cuda.current_stream(self.dev)
         side = self.comm_stream
+        side_h = ctypes.c_void_p(side.cuda_stream)
         Ln = eng.layers
-        ng = max(1, min(Ln, int(os.environ.get("MAGB200_ALLREDUCE_GROUPS", "6"))))
+        ng = max(1, min(Ln, int(os.environ.get("MAGB200_ALLREDUCE_GROUPS", "12"))))
         cuts = sorted({(k * Ln) // ng for k in range(ng + 1)}, reverse=True)  # e.g. 12, 10, 8, 6, 4, 2, 0
         groups = [(cuts[k + 1], cuts[k]) for k in range(len(cuts) - 1)]       # [(8,12), (4,8), (0,4)]
         args = (self.train_dims, self.ws, i["input_ids"], i["token_type_ids"], i["attention_mask"], self.dlogits,
                 self.grads)
+        total = eng.layout.total
+        tail0 = int(eng.offsets[L.OFF_POOL_W])
         for gi, (lo, hi) in enumerate(groups):
             last = gi == len(groups) - 1
             eng.backward_part(*args, hi - 1, lo, (1 if gi == 0 else 0) | (2 if last else 0))
-            if not last:
-                ev = torch.cuda.Event()
-                ev.record(main)
-                side.wait_event(ev)
-                s, e = eng.layer_grad_range(lo, hi)
-                with torch.cuda.stream(side):
-                    allreduce_sum_(self.grads[s:e], self.pg)
-        # what is left: embeddings + the first group of layers, and pooler / MAG / classifier at the end
-        lo0, hi0 = groups[-1]
-        s, e = eng.layer_grad_range(lo0, hi0)
-        if self.sparse_embedding_allreduce:
-            # the word-embedding gradient is non-zero in <= B*S of its 30522 rows: exchange (ids, rows) instead of
-            # all-reducing 94 MB (parallel.sparse_rows_allreduce_; opt-in until measured at N = 8)
-            w0, w1 = int(eng.offsets[L.OFF_WORD]), int(eng.offsets[L.OFF_POS])
-            table = self.grads[w0:w0 + eng.vocab * eng.hidden].view(eng.vocab, eng.hidden)
-            sparse_rows_allreduce_(table, i["input_ids"], self.pg)
-            allreduce_sum_(self.grads[w1:e], self.pg)
-        else:
-            allreduce_sum_(self.grads[:e], self.pg)
-        allreduce_sum_(self.grads[int(eng.offsets[L.OFF_POOL_W]):], self.pg)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            s, e = eng.layer_grad_range(lo, hi)
+            with torch.cuda.stream(side):
+                allreduce_sum_(self.grads[s:e], self.pg)
+                if self.bucket_adamw:
+                    self._adamw_range(s, e, side_h)
+        # the bottom of the network (all produced by the last piece): embeddings in front, pooler / MAG / classifier behind
+        lo0 = eng.layer_grad_range(groups[-1][0], groups[-1][1])[0]
+        with torch.cuda.stream(side):
+            if self.sparse_embedding_allreduce:
+                w0, w1 = int(eng.offsets[L.OFF_WORD]), int(eng.offsets[L.OFF_POS])
+                table = self.grads[w0:w0 + eng.vocab * eng.hidden].view(eng.vocab, eng.hidden)
+                sparse_rows_allreduce_(table, i["input_ids"], self.pg)
+                allreduce_sum_(self.grads[w1:lo0], self.pg)
+            else:
+                allreduce_sum_(self.grads[:lo0], self.pg)
+            allreduce_sum_(self.grads[tail0:], self.pg)
+            if self.bucket_adamw:
+                self._adamw_range(0, lo0, side_h)
+                self._adamw_range(tail0, total, side_h)
         main.wait_stream(side)
 
     def release(self):

@@ -23,18 +23,20 @@ import torch
 from . import hf302_shim as shim
 from . import inputs as gen
 from . import weights
+from .fingerprint import project
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
 
 def grad_fingerprint(named_grads):
-    """Per-parameter (l2 norm, sum, first 8 elements) -- small but position-sensitive."""
+    """Per-parameter (l2 norm, sum, first 8 elements, 4 random projections) -- small but position-sensitive."""
     out = {}
     for k, g in named_grads.items():
         g = g.detach().double().flatten()
         out["gnorm/" + k] = np.float64(g.norm().item())
         out["gsum/" + k] = np.float64(g.sum().item())
         out["ghead/" + k] = g[:8].float().numpy()
+        out["gproj/" + k] = project(k, g.numpy())
     return out
 
 
@@ -129,7 +131,8 @@ def edge_cases():
     sequence, XLNet rows that are all padding except two), batch 1, and BERT's maximum sequence length."""
     make_bert("bert_mosi_minlen_b4", 4, 47, 74, 0, 77, True, True, lens=[2, 3, 50, 2])
     make_bert("bert_mosi_b1", 1, 47, 74, 0, 78, False, True)
-    make_bert("bert_mosi_s512_b2", 2, 47, 74, 0, 79, False, False, keep_rows=0, seq=512, lens=[512, 300])   # logits/pooled only
+    make_bert("bert_mosi_s512_b2", 2, 47, 74, 0, 79, False, True, keep_rows=0, seq=512, lens=[512, 300])    # configs[4] length
+    make_bert("bert_mosi_s128_b4", 4, 47, 74, 0, 81, False, True, keep_rows=0, seq=128, lens=[128, 65, 100, 7])
     make_xlnet("xlnet_mosi_minlen_b4", 4, 47, 74, 0, 80, False, True, lens=[2, 3, 50, 2])
 
 
@@ -145,7 +148,7 @@ def main():
     make_mag("mag_mosei", 35, 74, 1.0, True, 1, 9, False)
     # configs[1] shape (MOSI) at bs=8 with grads, and at the full bs=48 forward-only
     make_bert("bert_mosi_b8", 8, 47, 74, 0, 1234, False, True)
-    make_bert("bert_mosi_b48", 48, 47, 74, 0, 1234, False, False)
+    make_bert("bert_mosi_b48", 48, 47, 74, 0, 1234, False, True)               # configs[1] itself, with gradients
     make_bert("bert_mosi_b8_reflike", 8, 47, 74, 0, 4321, True, True)          # zero biases -> guard rows
     # configs[2] shape (MOSEI, V=35)
     make_bert("bert_mosei_b8", 8, 35, 74, 1, 1234, False, True)

@@ -160,9 +160,15 @@ def xlnet_layer(sd, i, h, pos_emb, key_pad, tt, n_head, drop=_identity, eps=1e-1
     v = (h @ Wv).view(B, S, n_head, d)
     # k_head_r: the reference projects pos_emb expanded over the batch (xlnet.py:332-333); the
     # projection does not depend on b (in eval mode), so project once.
-    kr = (pos_emb @ Wr).view(2 * S, n_head, d)
+    # In training mode the reference drops the batch-expanded pos_emb (xlnet.py:332-333), so every batch element
+    # sees its own mask: pos_emb may then be [B, 2S, H] (tests inject the kernels' masks that way).
     ac = torch.einsum("bind,bjnd->bnij", q + sd[p + "r_w_bias"], k)
-    bd_raw = torch.einsum("bind,pnd->bnip", q + sd[p + "r_r_bias"], kr)          # [B,n,S,2S]
+    if pos_emb.dim() == 3:
+        kr = (pos_emb @ Wr).view(B, 2 * S, n_head, d)
+        bd_raw = torch.einsum("bind,bpnd->bnip", q + sd[p + "r_r_bias"], kr)     # [B,n,S,2S]
+    else:
+        kr = (pos_emb @ Wr).view(2 * S, n_head, d)
+        bd_raw = torch.einsum("bind,pnd->bnip", q + sd[p + "r_r_bias"], kr)      # [B,n,S,2S]
     # rel_shift_bnij: shifted[i, j] = raw[i, j + S - i]   (verified against HF)
     ii = torch.arange(S, device=h.device)[:, None]
     jj = torch.arange(S, device=h.device)[None, :]

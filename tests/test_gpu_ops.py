@@ -40,7 +40,7 @@ def _g(seed=0):
     # accumulate-into-residual dgrad and N = 768 forward shapes, a shape with fewer tiles than clusters, ragged M / K
     (3072, 768, 2400, 1, 1, "atomic"), (2304, 768, 2400, 1, 1, "atomic"), (2400, 768, 3072, 0, 1, "atomic"),
     (2400, 768, 3072, 0, 0, "atomic"), (2400, 768, 768, 0, 0, "atomic"), (300, 256, 200, 0, 0, "atomic"),
-    (100, 96, 64, 0, 0, "atomic"),
+    (100, 128, 64, 0, 0, "atomic"),
 ])
 def test_gemm(M, N, K, a_mn, b_mn, epi):
     g = _g(1)

@@ -173,6 +173,46 @@ def test_xlnet_full_gradient_against_oracle_and_train_mode_runs():
     assert all(torch.isfinite(p.grad).all() for k, p in model.named_parameters() if p.grad is not None)
 
 
+def test_xlnet_training_mode_matches_oracle_with_the_kernels_dropout_masks():
+    """Dropout on at every site of MAG_XLNetModel.forward (word embeddings xlnet.py:304-305, the batch-expanded position
+    embeddings :332-333, MAG, attention probabilities / attention output / FFN activation / FFN output per layer, the
+    final output :396, the summary): the oracle is fed the exact keep-masks the kernels generate."""
+    layers, B, S = 2, 4, 50
+    model, sd = make_xlnet(layers, seed=3)
+    model.train()
+    b = gen.xlnet_batch(B, S, seed=12)
+    cb = to_cuda(b)
+    torch.manual_seed(123)
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    torch.manual_seed(123)
+    loss = _forward(model, cb, labels=cb["labels"])[0]
+    loss.backward()
+    sites = {"emb": (1, (B, S, 768), 0.1), "mag": (2, (B, S, 768), 0.5), "pooled": (3, (B, 768), 0.1),
+             "pos": (4, (B, 2 * S, 768), 0.1), "final": (5, (B, S, 768), 0.1)}
+    for l in range(layers):
+        sites[f"L{l}.attn_prob"] = (16 + 4 * l, (B, 12, S, S), 0.1)
+        sites[f"L{l}.attn_out"] = (17 + 4 * l, (B, S, 768), 0.1)
+        sites[f"L{l}.ffn_out"] = (18 + 4 * l, (B, S, 768), 0.1)
+        sites[f"L{l}.ffn_mid"] = (19 + 4 * l, (B, S, 3072), 0.1)
+    masks = {k: (keep_mask(shape, p, seed, site).cpu(), p) for k, (site, shape, p) in sites.items()}
+
+    def drop(site, x):
+        m, p = masks[site]
+        return x * m / (1 - p)            # "pos": [2S, H] * [B, 2S, H] -> one dropped copy per batch element
+
+    ref_sd = {k: (v.clone().requires_grad_(True) if k != "transformer.mask_emb" else v) for k, v in sd.items()}
+    ref = R.mag_xlnet_forward(ref_sd, b["input_ids"], b["visual"], b["acoustic"], b["attention_mask"], b["token_type_ids"],
+                              n_layer=layers, drop=drop)
+    ref_loss = R.mse_loss(ref, b["labels"])
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) < 5e-3 * max(1.0, abs(ref_loss.item()))
+    named = dict(model.named_parameters())
+    for k in ("logits_proj.weight", "transformer.layer.1.ff.layer_2.weight", "transformer.layer.0.rel_attn.q",
+              "transformer.layer.1.rel_attn.r", "transformer.layer.0.rel_attn.r_r_bias", "transformer.MAG.W_hv.weight",
+              "transformer.layer.1.ff.layer_1.weight", "transformer.word_embedding.weight"):
+        assert rel_err(named[k].grad, ref_sd[k].grad) < 4e-2, (k, rel_err(named[k].grad, ref_sd[k].grad))
+
+
 def test_xlnet_api_contract():
     model, _ = make_xlnet(2, seed=1)
     model.eval()

@@ -133,3 +133,21 @@ def test_xlnet_edge_case_matches_reference_golden(golden_dir):
     assert np.abs(want["mag"][:2].detach().numpy() - g["mag"]).max() < 1e-4
     loss.backward()
     _check_grads(g, {k: v.grad for k, v in sd.items() if v.grad is not None})
+
+
+def test_oracle_full_tensor_gradient_error_is_at_rounding_level(golden_dir):
+    """The restatement's autograd gradients against the verbatim reference through the random-projection fingerprints
+    (oracle/fingerprint.py): a full-tensor relative error estimate for all 211 tensors of MAG-BERT."""
+    from oracle.fingerprint import projection_error
+    g = np.load(os.path.join(golden_dir, "bert_mosi_b8.npz"))
+    B, V, A, wseed, iseed, reflike = [int(x) for x in g["args"]]
+    sd = weights.bert_state_dict(visual_dim=V, acoustic_dim=A, seed=wseed, reference_like=bool(reflike))
+    ref_sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    b = gen.bert_batch(B, 50, V, A, seed=iseed)
+    out = R.mag_bert_forward(ref_sd, b["input_ids"], b["visual"], b["acoustic"], b["attention_mask"], b["token_type_ids"])
+    R.mse_loss(out, b["labels"]).backward()
+    for k, v in ref_sd.items():
+        ref_norm = float(g["gnorm/" + k])
+        if ref_norm < 1e-7:
+            continue
+        assert projection_error(k, v.grad.numpy(), g["gproj/" + k], ref_norm) < 2e-4, k
