@@ -1,20 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- MAG-BERT samples/s (seq=50, bs=48 per GPU) on N B200s, BASELINE.json's metric.
 
-    python bench.py --gpus 1 --steps 200 --warmup 10                 # our arm
+    python bench.py --gpus 1 --steps 200 --warmup 10                 # our arm (BASELINE.json configs[1])
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W       # N GPUs, one rank per GPU (NCCL)
     python bench.py --impl reference --gpus 1 --steps K --warmup W   # reference arm: the CPU oracle port
+    python bench.py --workload {mosi48,mosei128,s512,xlnet48} ...    # the other BASELINE.json configurations
 
 A "step" is one optimisation step (forward + MSE + backward + AdamW, dropout on) of
-MAG_BertForSequenceClassification (bert-base geometry, random init, synthetic MOSI-shaped batch:
-seq 50, V 47, A 74, bs 48 per GPU) -- the unit the reference's train_epoch executes
-(multimodal_driver.py:354-388).  One JSON line is printed by rank 0:
+MAG_BertForSequenceClassification / MAG_XLNetForSequenceClassification (base geometry, random init, synthetic
+MOSI/MOSEI-shaped batch) -- the unit the reference's train_epoch executes (multimodal_driver.py:354-388).
+One JSON line is printed by rank 0:
 
-  value      whole-job samples/s with the batch already resident in HBM (CUDA-graph replay, no copies)
-  e2e        the same through the public API with HOST batches: pinned-host -> H2D -> step -> loss D2H
-  roofline   the dominant kernel (tcgen05 GEMM, FFN-in shape) timed alone with CUDA events vs the measured
-             bf16/fp16 dense peak (MEASURED_PEAKS.json), plus per-shape entries and the whole-step fraction
+  value         whole-job samples/s with the batch already resident in HBM (CUDA-graph replay, no copies)
+  e2e           the same through the trainer API with HOST batches: pinned-host -> H2D -> step -> loss D2H
+  e2e_class_api the same through the reference-shaped class API, exactly the loop of multimodal_driver.py:359-386:
+                batch.to(DEVICE), model(...)[0], MSELoss, loss.backward(), optimizer.step(), scheduler.step(),
+                optimizer.zero_grad(), loss.item() -- with the drop-in AdamW tools/run_driver.py installs
+  roofline      the GEMM family timed alone with CUDA events on every shape of the step (forward, dgrad, wgrad; cold
+                operands) vs the measured bf16/fp16 dense peak (MEASURED_PEAKS.json); `kernel` is the shape with the
+                largest share of the step; plus the whole-step fraction
   cpu_baseline  oracle/restatement.py (torch fp32 on the host cores) on a bounded sample of the same workload
 """
 from __future__ import annotations
@@ -29,10 +34,26 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-SEQ, BS, V, A = 50, 48, 47, 74
-FWD_FLOP_PER_SAMPLE = 8.7234e9            # SURVEY.md section 8d (S=50, MOSI), algorithmic, padding not counted
-TRAIN_FLOP_PER_SAMPLE = 3 * FWD_FLOP_PER_SAMPLE
-METRIC = "MAG-BERT train-step samples/sec (seq=50, bs=48/GPU)"
+# name -> model family, seq, per-GPU batch at N GPUs, V, A, forward FLOP per sample, scaling
+WORKLOADS = {
+    "mosi48": dict(family="bert", seq=50, V=47, A=74, fwd_flop=8.7234e9, scaling="weak", per_gpu=lambda n: 48,
+                   desc="MAG-BERT bert-base-uncased geometry, MOSI-synthetic (seq=50, V=47, A=74), bs=48/GPU, train step = "
+                        "fwd + MSE + bwd + AdamW, dropout on (BASELINE.json configs[1])",
+                   metric="MAG-BERT train-step samples/sec (seq=50, bs=48/GPU)"),
+    "mosei128": dict(family="bert", seq=50, V=35, A=74, fwd_flop=8.7215e9, scaling="strong", per_gpu=lambda n: 128 // n,
+                     desc="MAG-BERT bert-base-uncased geometry, MOSEI-synthetic (seq=50, V=35, A=74), global bs=128 sharded "
+                          "over the GPUs, train step = fwd + MSE + bwd + all-reduce + AdamW, dropout on (BASELINE.json "
+                          "configs[2])",
+                     metric="MAG-BERT MOSEI train-step samples/sec (seq=50, global bs=128)"),
+    "s512": dict(family="bert", seq=512, V=47, A=74, fwd_flop=98.036e9, scaling="weak", per_gpu=lambda n: 32,
+                 desc="MAG-BERT bert-base-uncased geometry, long-sequence stress (seq=512, V=47, A=74), bs=32/GPU (global 256 "
+                      "on 8 GPUs), train step = fwd + MSE + bwd + AdamW, dropout on (BASELINE.json configs[4])",
+                 metric="MAG-BERT long-sequence train-step samples/sec (seq=512, bs=32/GPU)"),
+    "xlnet48": dict(family="xlnet", seq=50, V=47, A=74, fwd_flop=10.095e9, scaling="weak", per_gpu=lambda n: 48,
+                    desc="MAG-XLNet xlnet-base-cased geometry, MOSI-synthetic (seq=50, V=47, A=74), bs=48/GPU, train step = "
+                         "fwd + MSE + bwd + AdamW, dropout on (BASELINE.json configs[3])",
+                    metric="MAG-XLNet train-step samples/sec (seq=50, bs=48/GPU)"),
+}
 
 
 def load_peaks():
@@ -103,18 +124,24 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------- CPU arm
-def cpu_oracle_throughput(train_samples_budget, batch, steps, warmup, mode="train"):
-    """Times oracle/restatement.py on the host cores.  Returns (samples/s, cores, description)."""
+def cpu_oracle_throughput(wl, batch, steps, warmup, mode="train"):
+    """Times oracle/restatement.py on the host cores.  Returns (samples/s, cores, seconds per step)."""
     import torch
     from oracle import inputs as gen, restatement as R, weights
-    sd = weights.bert_state_dict(seed=0)
-    cores = pick_cpu_threads(torch, R, gen, sd)
-    b = gen.bert_batch(batch, SEQ, V, A, seed=1234)
+    bert = wl["family"] == "bert"
+    if bert:
+        sd = weights.bert_state_dict(visual_dim=wl["V"], acoustic_dim=wl["A"], seed=0)
+        b = gen.bert_batch(batch, wl["seq"], wl["V"], wl["A"], seed=1234)
+        fwd = R.mag_bert_forward
+    else:
+        sd = weights.xlnet_state_dict(visual_dim=wl["V"], acoustic_dim=wl["A"], seed=0)
+        b = gen.xlnet_batch(batch, wl["seq"], wl["V"], wl["A"], seed=1234)
+        fwd = R.mag_xlnet_forward
+    cores = pick_cpu_threads(torch, fwd, gen, sd, wl)
     if mode == "train":
-        params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-        plist = list(params.values())
+        params = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+        plist = [p for p in params.values() if p.requires_grad]
         opt = torch.optim.AdamW(plist, lr=1e-5, eps=1e-6, weight_decay=0.01)
-        gens = torch.Generator().manual_seed(0)
 
         def drop(site, x):   # the reference trains with dropout on (p = 0.1 / 0.5 for MAG)
             p = 0.5 if site == "mag" else 0.1
@@ -122,8 +149,8 @@ def cpu_oracle_throughput(train_samples_budget, batch, steps, warmup, mode="trai
 
         def step():
             opt.zero_grad(set_to_none=True)
-            logits = R.mag_bert_forward(params, b["input_ids"], b["visual"], b["acoustic"], b["attention_mask"],
-                                        b["token_type_ids"], drop=drop)
+            logits = fwd(params, b["input_ids"], b["visual"], b["acoustic"], b["attention_mask"], b["token_type_ids"],
+                         drop=drop)
             loss = R.mse_loss(logits, b["labels"])
             loss.backward()
             opt.step()
@@ -131,8 +158,7 @@ def cpu_oracle_throughput(train_samples_budget, batch, steps, warmup, mode="trai
     else:
         def step():
             with torch.no_grad():
-                R.mag_bert_forward(sd, b["input_ids"], b["visual"], b["acoustic"], b["attention_mask"],
-                                   b["token_type_ids"])
+                fwd(sd, b["input_ids"], b["visual"], b["acoustic"], b["attention_mask"], b["token_type_ids"])
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
@@ -142,20 +168,21 @@ def cpu_oracle_throughput(train_samples_budget, batch, steps, warmup, mode="trai
     return batch * steps / dt, cores, dt / steps
 
 
-def pick_cpu_threads(torch, R, gen, sd):
+def pick_cpu_threads(torch, fwd, gen, sd, wl):
     """The CPU arm should be as fast as the host allows: torch's intra-op pool does not scale to every
-    hardware thread on small matrices, so time one eval forward of 8 sequences at a few thread counts and
+    hardware thread on small matrices, so time one eval forward of a few sequences at a few thread counts and
     keep the best (all cores are always among the candidates)."""
     ncpu = os.cpu_count() or 1
     cands = sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu} | {ncpu})
-    b = gen.bert_batch(8, SEQ, V, A, seed=7)
+    mk = gen.bert_batch if wl["family"] == "bert" else gen.xlnet_batch
+    b = mk(8 if wl["seq"] <= 64 else 2, wl["seq"], wl["V"], wl["A"], seed=7)
     best, best_t = ncpu, float("inf")
     for c in cands:
         torch.set_num_threads(c)
         with torch.no_grad():
-            R.mag_bert_forward(sd, b["input_ids"], b["visual"], b["acoustic"], b["attention_mask"], b["token_type_ids"])
+            fwd(sd, b["input_ids"], b["visual"], b["acoustic"], b["attention_mask"], b["token_type_ids"])
             t0 = time.perf_counter()
-            R.mag_bert_forward(sd, b["input_ids"], b["visual"], b["acoustic"], b["attention_mask"], b["token_type_ids"])
+            fwd(sd, b["input_ids"], b["visual"], b["acoustic"], b["attention_mask"], b["token_type_ids"])
             dt = time.perf_counter() - t0
         if dt < best_t:
             best, best_t = c, dt
@@ -174,23 +201,27 @@ def cpu_model_name():
     return "unknown"
 
 
-def run_reference_arm(args):
+def cpu_sample_size(wl, steps, warmup):
+    """Sequences per CPU step so that the whole run stays within a few minutes (~30 sequences/s at S=50)."""
+    budget = 1500 if wl["seq"] <= 64 else 48
+    return max(1, min(wl["per_gpu"](1), int(budget / max(1, steps + warmup))))
+
+
+def run_reference_arm(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded sample: keep the whole run within a few minutes of CPU time
-    per_step = max(1, min(BS, int(1500 / max(1, args.steps + args.warmup))))
-    sps, cores, sec = cpu_oracle_throughput(0, per_step, args.steps, args.warmup, "train")
+    per_step = cpu_sample_size(wl, args.steps, args.warmup)
+    sps, cores, sec = cpu_oracle_throughput(wl, per_step, args.steps, args.warmup, "train")
+    sample = (f"{args.steps} timed + {args.warmup} warm-up train steps of {per_step} sequences (oracle/restatement.py, torch fp32, "
+              f"{cores} threads, {cpu_model_name()})")
     line = {
-        "impl": "reference", "metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": wl["metric"], "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"MAG-BERT bert-base MOSI-synthetic train step (fwd+MSE+bwd+AdamW, dropout on) seq={SEQ} "
-                               f"V={V} A={A}; CPU sample of {per_step} sequences per step", "global_batch": per_step,
-                   "seq_len": SEQ, "parallelism": "cpu"},
-        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} timed train steps of {per_step} sequences (oracle/restatement.py, torch "
-                                   f"fp32, {cores} threads, {cpu_model_name()})"},
+        "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "global_batch": per_step, "seq_len": wl["seq"], "parallelism": "cpu",
+                   "cpu_sample": f"{per_step} sequences per step"},
+        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -198,31 +229,51 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
+def gemm_shapes(T, H=768, I=3072):
+    """(name, role, per-step count (12 layers), M, N, K, a_mn, b_mn, epilogue) of every encoder GEMM of a train step."""
+    return [
+        ("fwd_qkv", "forward", 12, T, 3 * H, H, 0, 0, "f16"),
+        ("fwd_attn_out", "forward", 12, T, H, H, 0, 0, "f32"),
+        ("fwd_ffn_in", "forward", 12, T, I, H, 0, 0, "gelu"),
+        ("fwd_ffn_out", "forward", 12, T, H, I, 0, 0, "f32"),
+        ("dgrad_ffn_out", "dgrad", 12, T, I, H, 0, 1, "dgelu"),       # dU = (dY W2) * gelu'(u)
+        ("dgrad_ffn_in", "dgrad", 12, T, H, I, 0, 1, "atomic"),       # residual gradient += dU W1
+        ("dgrad_attn_out", "dgrad", 12, T, H, H, 0, 1, "f16"),
+        ("dgrad_qkv", "dgrad", 12, T, H, 3 * H, 0, 1, "atomic"),
+        ("wgrad_ffn_out", "wgrad", 12, H, I, T, 1, 1, "atomic"),      # dW2[768, 3072] += dY^T G
+        ("wgrad_ffn_in", "wgrad", 12, I, H, T, 1, 1, "atomic"),
+        ("wgrad_attn_out", "wgrad", 12, H, H, T, 1, 1, "atomic"),
+        ("wgrad_qkv", "wgrad", 12, 3 * H, H, T, 1, 1, "atomic"),
+    ]
+
+
 def time_gemm_shapes(torch, L, lib, peaks, T):
-    """The tcgen05 GEMM alone on the step's four forward shapes (CUDA events, back-to-back launches over
-    rotating buffers larger than L2)."""
-    shapes = [("ffn_in", T, 3072, 768, L.EPI_GELU_F16), ("ffn_out", T, 768, 3072, L.EPI_STORE_F32),
-              ("qkv", T, 2304, 768, L.EPI_STORE_F16), ("attn_out", T, 768, 768, L.EPI_STORE_F32)]
+    """The tcgen05 GEMM alone on every encoder shape of the step (CUDA events on the launching stream, back-to-back
+    launches over rotating buffers larger than L2: cold operands)."""
     out = []
     st = L.current_stream()
-    for name, M, N, K, epi in shapes:
-        nbuf = 12   # 12 x (A + W + out) > 126 MB L2 for every shape
-        As = [torch.randn(M, K, device="cuda").half() for _ in range(nbuf)]
-        Ws = [(torch.randn(N, K, device="cuda") * 0.02).half() for _ in range(nbuf)]
-        bias = torch.zeros(N, device="cuda")
-        o_dt = torch.float32 if epi == L.EPI_STORE_F32 else torch.float16
-        Os = [torch.empty(M, N, device="cuda", dtype=o_dt) for _ in range(nbuf)]
-        O1 = torch.empty(M, N, device="cuda", dtype=torch.float16)
+    epis = {"f16": L.EPI_STORE_F16, "f32": L.EPI_STORE_F32, "gelu": L.EPI_GELU_F16, "dgelu": L.EPI_DGELU_F16,
+            "atomic": L.EPI_ATOMIC_F32}
+    for name, role, count, M, N, K, a_mn, b_mn, epi_name in gemm_shapes(T):
+        epi = epis[epi_name]
+        per = (M * K + N * K) * 2 + M * N * (4 if epi_name in ("f32", "atomic") else 2) * (2 if epi_name in ("gelu", "dgelu") else 1)
+        nbuf = max(3, min(16, int(160e6 // per) + 1))       # rotating set > 126 MB L2
+        As = [(torch.randn(K, M, device="cuda") if a_mn else torch.randn(M, K, device="cuda")).half() for _ in range(nbuf)]
+        Bs = [((torch.randn(K, N, device="cuda") if b_mn else torch.randn(N, K, device="cuda")) * 0.02).half() for _ in range(nbuf)]
+        bias = torch.zeros(N, device="cuda") if role == "forward" else None
+        o_dt = torch.float32 if epi_name in ("f32", "atomic") else torch.float16
+        Os = [torch.zeros(M, N, device="cuda", dtype=o_dt) for _ in range(nbuf)]
+        O1 = torch.empty(M, N, device="cuda", dtype=torch.float16) if epi_name == "gelu" else None
+        aux = torch.ones(M, N, device="cuda", dtype=torch.float16) if epi_name == "dgelu" else None
 
         def launch(i):
             j = i % nbuf
-            L.check(lib.magb200_gemm(L.ptr(As[j]), L.ptr(Ws[j]), M, N, K, K, K, L.F16, L.F16, 0, 0, epi, L.ptr(bias),
-                                     L.ptr(Os[j]), L.ptr(O1) if epi == L.EPI_GELU_F16 else None, None, N, 1.0, 1, 0, 0,
-                                     st))
+            L.check(lib.magb200_gemm(L.ptr(As[j]), L.ptr(Bs[j]), M, N, K, As[j].shape[1], Bs[j].shape[1], L.F16, L.F16, a_mn,
+                                     b_mn, epi, L.ptr(bias), L.ptr(Os[j]), L.ptr(O1), L.ptr(aux), N, 1.0, 1, 0, 0, st))
         for i in range(nbuf):
             launch(i)
         torch.cuda.synchronize()
-        reps = 60
+        reps = 48
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(reps):
@@ -230,12 +281,12 @@ def time_gemm_shapes(torch, L, lib, peaks, T):
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / reps
-        flops = 2.0 * M * N * K
-        tf = flops / (us * 1e-6) / 1e12
-        # forward Linears run on the persistent cta_group::2 kernel (profiles/r01_gemm_policy.txt)
-        kern = "gemm2p_tcgen05_kernel<256x%d pair tiles>" % (256 if (N % 256 == 0 and N >= 1024) else 128)
-        out.append({"kernel": kern, "shape": name, "M": M, "N": N, "K": K, "us": round(us, 2),
-                    "achieved": round(tf, 1), "frac": round(tf / peaks["tflops_burst"], 4)})
+        tf = 2.0 * M * N * K / (us * 1e-6) / 1e12
+        out.append({"shape": name, "role": role, "per_step": count, "M": M, "N": N, "K": K,
+                    "operands": ("MN" if a_mn else "K") + "/" + ("MN" if b_mn else "K") + "-major", "epilogue": epi_name,
+                    "us": round(us, 2), "achieved": round(tf, 1), "frac": round(tf / peaks["tflops_burst"], 4),
+                    "step_share_us": round(us * count, 1)})
+        del As, Bs, Os, O1, aux
     return out
 
 
@@ -244,16 +295,74 @@ def read_profile_traffic():
     if os.path.exists(p):
         try:
             with open(p) as fh:
-                return json.load(fh).get("ffn_in_dram_bytes_per_launch")
+                return json.load(fh)
         except Exception:
             return None
     return None
 
 
-def run_gpu_arm(args):
+def make_model(torch, wl, device):
+    import contextlib
+    import io
+    import global_configs
+    global_configs.VISUAL_DIM, global_configs.ACOUSTIC_DIM = wl["V"], wl["A"]
+
+    class MC:
+        beta_shift, dropout_prob = 1.0, 0.5
+
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        if wl["family"] == "bert":
+            from transformers import BertConfig
+            import bert as mag_bert
+            model = mag_bert.MAG_BertForSequenceClassification(BertConfig(num_labels=1), MC())
+        else:
+            from transformers import XLNetConfig
+            import xlnet as mag_xlnet
+            cfg = XLNetConfig(vocab_size=32000, d_model=768, n_layer=12, n_head=12, d_inner=3072, mem_len=None, num_labels=1)
+            model = mag_xlnet.MAG_XLNetForSequenceClassification(cfg, MC())
+    return model.to(device).train()
+
+
+def class_api_loop(torch, model, batch, device, steps, warmup, total_steps):
+    """multimodal_driver.py:328-386 in shape (see the module docstring).  Returns (seconds for `steps` steps, last loss,
+    fused optimizer steps taken)."""
+    from transformers import get_linear_schedule_with_warmup
+    from bert_multimodal_transformer_b200.optim import AdamW
+    named = list(model.named_parameters())
+    no_decay = ["bias", "LayerNorm.bias", "LayerNorm.weight"]
+    groups = [{"params": [p for n, p in named if not any(nd in n for nd in no_decay)], "weight_decay": 0.01},
+              {"params": [p for n, p in named if any(nd in n for nd in no_decay)], "weight_decay": 0.0}]
+    optimizer = AdamW(groups, lr=1e-5)
+    scheduler = get_linear_schedule_with_warmup(optimizer, num_warmup_steps=0.1 * total_steps, num_training_steps=total_steps)
+    host = tuple(batch[k] for k in ("input_ids", "visual", "acoustic", "attention_mask", "token_type_ids", "labels"))
+    loss_fct = torch.nn.MSELoss()
+    model.train()
+
+    def one():
+        b = tuple(t.to(device) for t in host)
+        input_ids, visual, acoustic, input_mask, segment_ids, label_ids = b
+        outputs = model(input_ids, visual, acoustic, token_type_ids=segment_ids, attention_mask=input_mask, labels=None)
+        loss = loss_fct(outputs[0].view(-1), label_ids.view(-1))
+        loss.backward()
+        v = loss.item()
+        optimizer.step()
+        scheduler.step()
+        optimizer.zero_grad()
+        return v
+    for _ in range(max(3, warmup)):
+        one()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        last = one()
+    torch.cuda.synchronize()
+    return time.perf_counter() - t0, last, optimizer.fused_steps_taken
+
+
+def run_gpu_arm(args, wl):
     import torch
     import torch.distributed as dist
-    from transformers import BertConfig
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -262,10 +371,10 @@ def run_gpu_arm(args):
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference for "
                          "the CPU oracle arm)")
     torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    import bert as mag_bert
+        dist.init_process_group("nccl", device_id=device)
     from bert_multimodal_transformer_b200 import _lib as L
     from bert_multimodal_transformer_b200.trainer import MagBertTrainer
     from oracle import inputs as gen
@@ -273,20 +382,18 @@ def run_gpu_arm(args):
     lib = L.load()
     L.check(lib.magb200_device_check())
     peaks = load_peaks()
+    SEQ, V, A = wl["seq"], wl["V"], wl["A"]
+    BS = wl["per_gpu"](world)
+    if BS < 1:
+        raise SystemExit(f"bench.py: workload {args.workload} cannot be sharded over {world} GPUs")
+    fwd_flop, train_flop = wl["fwd_flop"], 3 * wl["fwd_flop"]
 
-    class MC:
-        beta_shift, dropout_prob = 1.0, 0.5
-
-    torch.manual_seed(0)
-    cfg = BertConfig(num_labels=1)
-    import io, contextlib
-    with contextlib.redirect_stdout(io.StringIO()):
-        model = mag_bert.MAG_BertForSequenceClassification(cfg, MC())
-    model = model.to(torch.device("cuda", local)).train()
-    total_steps = args.steps * 2 + args.warmup * 2 + 64
+    model = make_model(torch, wl, device)
+    total_steps = args.steps * 3 + args.warmup * 3 + 64
     trainer = MagBertTrainer(model, BS, SEQ, lr=1e-5, weight_decay=0.01, warmup_steps=total_steps // 10,
                              total_steps=total_steps, use_cuda_graph=not args.no_graph, seed=rank)
-    batch = gen.bert_batch(BS, SEQ, V, A, seed=1234 + rank)
+    mk = gen.bert_batch if wl["family"] == "bert" else gen.xlnet_batch
+    batch = mk(BS, SEQ, V, A, seed=1234 + rank)
     trainer._stage(batch["input_ids"], batch["visual"], batch["acoustic"], batch["attention_mask"],
                    batch["token_type_ids"], batch["labels"])
     trainer.upload_staged()     # "value" runs on this HBM-resident batch
@@ -295,6 +402,13 @@ def run_gpu_arm(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
 
     # launches per step (counted by the library while the step is recorded / run once)
     c0 = lib.magb200_launch_count()
@@ -317,11 +431,7 @@ def run_gpu_arm(args):
             e1.record()
         trainer.stream.synchronize()
     barrier()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = max_over_ranks(e0.elapsed_time(e1))
     value = world * BS * args.steps / (ms * 1e-3)
     loss_after = float(trainer.loss.item())
     if args.profile_mode:
@@ -354,11 +464,7 @@ def run_gpu_arm(args):
         e1.record()
     trainer.stream.synchronize()
     wall = time.perf_counter() - t0
-    ms_e2e = max(e0.elapsed_time(e1), wall * 1e3)
-    if world > 1:
-        t = torch.tensor([ms_e2e], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
+    ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), wall * 1e3))
     e2e_value = world * BS * args.steps / (ms_e2e * 1e-3)
 
     # ---------------- eval forward (secondary number)
@@ -373,48 +479,63 @@ def run_gpu_arm(args):
     with torch.cuda.stream(trainer.stream):
         e1.record()
     trainer.stream.synchronize()
-    ms_eval = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms_eval], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_eval = float(t.item())
+    ms_eval = max_over_ranks(e0.elapsed_time(e1))
     eval_value = world * BS * n_eval / (ms_eval * 1e-3)
+
+    # ---------------- the reference-shaped class API (single process only: the driver has no DDP wrapper)
+    class_api = None
+    if world == 1 and not args.no_class_api:
+        torch.cuda.set_stream(torch.cuda.default_stream())
+        n_api = max(10, min(args.steps, 100))
+        sec, api_loss, fused = class_api_loop(torch, model, batch, device, n_api, 3, total_steps)
+        class_api = {"value": round(BS * n_api / sec, 1), "unit": "samples/s", "ms_per_step": round(sec / n_api * 1e3, 4),
+                     "steps": n_api, "h2d_bytes_per_step": trainer.h2d_bytes - 16, "d2h_bytes_per_step": 4,
+                     "fused_optimizer_steps": int(fused), "last_loss": api_loss,
+                     "api": "multimodal_driver.py:359-386 loop: batch.to(DEVICE); model(...)[0]; MSELoss; loss.backward(); "
+                            "loss.item(); AdamW.step() (bert_multimodal_transformer_b200.optim.AdamW, the class "
+                            "tools/run_driver.py installs as transformers.optimization.AdamW); scheduler.step(); zero_grad()"}
 
     if rank != 0:
         if world > 1:
             finish_distributed(trainer, dist)
         return
 
-    # ---------------- rank 0 only: dominant-kernel roofline + CPU baseline
+    # ---------------- rank 0 only: GEMM-family roofline + CPU baseline
     torch.cuda.set_stream(torch.cuda.default_stream())
     kernels = time_gemm_shapes(torch, L, lib, peaks, BS * SEQ)
-    dom = kernels[0]
+    dom = max(kernels, key=lambda k: k["step_share_us"])
+    gemm_us = sum(k["step_share_us"] for k in kernels)
+    gemm_flop = sum(2.0 * k["M"] * k["N"] * k["K"] * k["per_step"] for k in kernels)
+    traffic = read_profile_traffic() or {}
     roofline = {
-        "bound": "tensor", "kernel": "gemm2p_tcgen05_kernel<fp16, K-major, persistent cta_group::2, 256x256 pair tiles> "
-                                     "(FFN-in: M=2400 N=3072 K=768, bias + GELU + saved GELU' epilogue)",
+        "bound": "tensor",
+        "kernel": f"tcgen05 GEMM family (gemm2p / gemm2 / gemm _tcgen05_kernel): {dom['shape']} M={dom['M']} N={dom['N']} "
+                  f"K={dom['K']} {dom['operands']}, epilogue {dom['epilogue']} -- the shape with the largest share of the "
+                  f"step ({dom['step_share_us']} us of {round(gemm_us, 1)} us of GEMM time)",
         "achieved": dom["achieved"], "peak": peaks["tflops_burst"], "unit": "TFLOP/s", "frac": dom["frac"],
-        "traffic": read_profile_traffic(), "peak_source": peaks["source"] + ", burst figure (kernel timed alone)",
+        "traffic": traffic.get("dram_bytes_per_launch"), "traffic_source": traffic.get("source"),
+        "peak_source": peaks["source"] + ", burst figure (kernel timed alone)",
+        "gemm_family": {"us_per_step_sum": round(gemm_us, 1), "achieved": round(gemm_flop / (gemm_us * 1e-6) / 1e12, 1),
+                        "frac": round(gemm_flop / (gemm_us * 1e-6) / 1e12 / peaks["tflops_burst"], 4)},
         "per_shape": kernels,
-        "whole_step": {"flop_per_sample": TRAIN_FLOP_PER_SAMPLE,
-                       "achieved_tflops": round(value / world * TRAIN_FLOP_PER_SAMPLE / 1e12, 2),
-                       "frac_of_sustained_peak": round(value / world * TRAIN_FLOP_PER_SAMPLE / 1e12
-                                                       / peaks["tflops_sustained"], 4)},
+        "whole_step": {"flop_per_sample": train_flop,
+                       "achieved_tflops": round(value / world * train_flop / 1e12, 2),
+                       "frac_of_sustained_peak": round(value / world * train_flop / 1e12 / peaks["tflops_sustained"], 4)},
     }
     cpu = None
     if not args.no_cpu_baseline:
-        sps, cores, sec = cpu_oracle_throughput(0, 16, 3, 1, "train")
+        cpu_bs = cpu_sample_size(wl, 5, 1)
+        sps, cores, sec = cpu_oracle_throughput(wl, cpu_bs, 5, 1, "train")
         cpu = {"value": round(sps, 2), "unit": "samples/s", "cores": cores, "kind": "port",
-               "sample": f"3 timed + 1 warm-up train steps of 16 sequences (oracle/restatement.py, torch fp32 on "
+               "sample": f"5 timed + 1 warm-up train steps of {cpu_bs} sequences (oracle/restatement.py, torch fp32 on "
                          f"{cores} threads of {cpu_model_name()})"}
     line = {
-        "metric": METRIC, "value": round(value, 1), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "metric": wl["metric"], "value": round(value, 1), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None,
+        "scaling": wl["scaling"], "vs_baseline": None,
         "dtype": "fp16 tensor-core operands; fp32 accumulate / residual stream / LayerNorm / softmax / master weights",
         "data": "synthetic",
-        "config": {"workload": f"MAG-BERT bert-base-uncased geometry, MOSI-synthetic (seq={SEQ}, V={V}, A={A}), "
-                               f"bs={BS}/GPU, train step = fwd + MSE + bwd + AdamW, dropout on (BASELINE.json configs[1])",
-                   "global_batch": BS * world, "seq_len": SEQ, "parallelism": f"dp{world}",
+        "config": {"workload": wl["desc"], "global_batch": BS * world, "seq_len": SEQ, "parallelism": f"dp{world}",
                    "l2": "no flush needed: each step streams ~2.5 GB (params, grads, Adam moments, activations) "
                          ">> 126 MB L2",
                    "cuda_graph": trainer.use_graph},
@@ -423,10 +544,11 @@ def run_gpu_arm(args):
                 "d2h_bytes_per_step": trainer.d2h_bytes, "ms_per_step": round(ms_e2e / args.steps, 4),
                 "api": "MagBertTrainer.submit_train_step(host tensors) / result(ticket) -> loss float, 2 pinned "
                        "staging slots (host stages batch k+1 while the GPU runs step k)"},
+        "e2e_class_api": class_api,
         "gpu_launches": int(launches_per_step * args.steps),
         "gpu_launches_per_step": int(launches_per_step),
         "eval_forward": {"value": round(eval_value, 1), "unit": "samples/s", "ms_per_step": round(ms_eval / n_eval, 4),
-                         "roofline_frac_of_sustained": round(eval_value / world * FWD_FLOP_PER_SAMPLE / 1e12
+                         "roofline_frac_of_sustained": round(eval_value / world * fwd_flop / 1e12
                                                              / peaks["tflops_sustained"], 4)},
         "roofline": roofline,
         "cpu_baseline": cpu,
@@ -456,15 +578,18 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="mosi48", choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-class-api", action="store_true")
     ap.add_argument("--profile-mode", action="store_true",
                     help="only run the warm-up + timed train steps (for ncu captures); prints a reduced line")
     args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
     if args.impl == "reference":
-        run_reference_arm(args)
+        run_reference_arm(args, wl)
     else:
-        run_gpu_arm(args)
+        run_gpu_arm(args, wl)
 
 
 if __name__ == "__main__":

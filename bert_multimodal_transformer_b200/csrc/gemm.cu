@@ -96,7 +96,8 @@ static int pdl_attr(cudaLaunchAttribute* a) {
 }
 
 template <int EB, bool A_MN, bool B_MN, int BN, int STAGES, int CL>
-static int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, dim3 grid, cudaStream_t st) {
+static int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmArgs& g, dim3 grid,
+                          cudaStream_t st) {
   using SM = GemmSmem<EB, A_MN, B_MN, BN, STAGES>;
   auto kern = gemm_tcgen05_kernel<EB, A_MN, B_MN, BN, STAGES, CL>;
   static bool configured = false;
@@ -116,7 +117,7 @@ static int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const Ge
     }
     na += pdl_attr(attr + na);
     cfg.attrs = attr; cfg.numAttrs = na;
-    MAGB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, g));
+    MAGB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, g));
   }
   MAGB_CHECK_CUDA(cudaGetLastError());
   count_launch();
@@ -124,12 +125,12 @@ static int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const Ge
 }
 
 template <int EB, int BN, int STAGES, int CL>
-static int launch_majors(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g,
-                         dim3 grid, cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch_variant<EB, false, false, BN, STAGES, CL>(ta, tb, g, grid, st);
-  if (!a_mn && b_mn) return launch_variant<EB, false, true, BN, STAGES, CL>(ta, tb, g, grid, st);
-  if (a_mn && !b_mn) return launch_variant<EB, true, false, BN, STAGES, CL>(ta, tb, g, grid, st);
-  return launch_variant<EB, true, true, BN, STAGES, CL>(ta, tb, g, grid, st);
+static int launch_majors(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
+                         const GemmArgs& g, dim3 grid, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch_variant<EB, false, false, BN, STAGES, CL>(ta, tb, to, g, grid, st);
+  if (!a_mn && b_mn) return launch_variant<EB, false, true, BN, STAGES, CL>(ta, tb, to, g, grid, st);
+  if (a_mn && !b_mn) return launch_variant<EB, true, false, BN, STAGES, CL>(ta, tb, to, g, grid, st);
+  return launch_variant<EB, true, true, BN, STAGES, CL>(ta, tb, to, g, grid, st);
 }
 
 // debug/tuning hooks (tools/gemm_tune.py): trace buffer and tile-configuration override
@@ -145,7 +146,8 @@ void gemm_set_debug(unsigned long long* trace, int cfg) { g_trace = trace; g_cfg
 // ---------------------------------------------------------------------------------------------
 // 2-CTA (cta_group::2) path
 template <bool A_MN, bool B_MN, int BN, int STAGES>
-static int launch2_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, dim3 grid, cudaStream_t st) {
+static int launch2_variant(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmArgs& g, dim3 grid,
+                           cudaStream_t st) {
   using SM = Gemm2Smem<BN, STAGES>;
   auto kern = gemm2_tcgen05_kernel<A_MN, B_MN, BN, STAGES>;
   static bool configured = false;
@@ -159,23 +161,24 @@ static int launch2_variant(const CUtensorMap& ta, const CUtensorMap& tb, const G
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1 + pdl_attr(attr + 1);
-  MAGB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, g));
+  MAGB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, g));
   MAGB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
 }
 template <int BN, int STAGES>
-static int launch2_majors(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, dim3 grid,
-                          cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch2_variant<false, false, BN, STAGES>(ta, tb, g, grid, st);
-  if (!a_mn && b_mn) return launch2_variant<false, true, BN, STAGES>(ta, tb, g, grid, st);
-  if (a_mn && !b_mn) return launch2_variant<true, false, BN, STAGES>(ta, tb, g, grid, st);
-  return launch2_variant<true, true, BN, STAGES>(ta, tb, g, grid, st);
+static int launch2_majors(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
+                          const GemmArgs& g, dim3 grid, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch2_variant<false, false, BN, STAGES>(ta, tb, to, g, grid, st);
+  if (!a_mn && b_mn) return launch2_variant<false, true, BN, STAGES>(ta, tb, to, g, grid, st);
+  if (a_mn && !b_mn) return launch2_variant<true, false, BN, STAGES>(ta, tb, to, g, grid, st);
+  return launch2_variant<true, true, BN, STAGES>(ta, tb, to, g, grid, st);
 }
 
 // Persistent 2-CTA kernel: as many clusters as fit on the device at once (queried per variant), never more than tiles.
 template <bool A_MN, bool B_MN, int BN, int STAGES, int NEPI>
-static int launch2p_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, cudaStream_t st) {
+static int launch2p_variant(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmArgs& g,
+                            cudaStream_t st) {
   using SM = Gemm2pSmem<BN, STAGES, NEPI>;
   auto kern = gemm2p_tcgen05_kernel<A_MN, B_MN, BN, STAGES, NEPI>;
   static int max_clusters[16] = {0};
@@ -201,18 +204,32 @@ static int launch2p_variant(const CUtensorMap& ta, const CUtensorMap& tb, const 
   const int total = g.tiles_m * g.tiles_n * g.splits;
   const int ncl = total < max_clusters[dev] ? total : max_clusters[dev];
   cfg.gridDim = dim3(2 * ncl, 1, 1);
-  MAGB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, g));
+  MAGB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, g));
   MAGB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
 }
 template <int BN, int STAGES, int NEPI>
-static int launch2p_majors(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g,
-                           cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch2p_variant<false, false, BN, STAGES, NEPI>(ta, tb, g, st);
-  if (!a_mn && b_mn) return launch2p_variant<false, true, BN, STAGES, NEPI>(ta, tb, g, st);
-  if (a_mn && !b_mn) return launch2p_variant<true, false, BN, STAGES, NEPI>(ta, tb, g, st);
-  return launch2p_variant<true, true, BN, STAGES, NEPI>(ta, tb, g, st);
+static int launch2p_majors(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
+                           const GemmArgs& g, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch2p_variant<false, false, BN, STAGES, NEPI>(ta, tb, to, g, st);
+  if (!a_mn && b_mn) return launch2p_variant<false, true, BN, STAGES, NEPI>(ta, tb, to, g, st);
+  if (a_mn && !b_mn) return launch2p_variant<true, false, BN, STAGES, NEPI>(ta, tb, to, g, st);
+  return launch2p_variant<true, true, BN, STAGES, NEPI>(ta, tb, to, g, st);
+}
+
+// Tensor map of the fp32 output for the TMA reduction epilogue (boxes of 32 rows x 32 columns, SWIZZLE_128B); for the
+// other epilogues the kernels never touch the third descriptor and a copy of A's is passed.
+static int g_tma_reduce = 1;   // MAGB200_TMA_REDUCE=0: per-lane red.global.add.v4.f32 (the round-1 epilogue)
+static int output_map(const GemmProblem& p, const CUtensorMap& fallback, CUtensorMap* to, GemmArgs* g) {
+  g->tma_reduce = 0;
+  *to = fallback;
+  if (p.epi != EPI_ATOMIC_F32 || !g_tma_reduce) return 0;
+  if ((reinterpret_cast<uintptr_t>(p.out0) & 15) != 0 || (p.ldo * 4) % 16 != 0) return 0;
+  int rc = get_tensor_map(to, p.out0, DT_F32, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldo, 32, 32);
+  if (rc) return rc;
+  g->tma_reduce = 1;
+  return 0;
 }
 
 static int gemm_launch_2cta(const GemmProblem& p, int BN, cudaStream_t st, bool persistent = false, bool stream_k = false) {
@@ -254,13 +271,16 @@ static int gemm_launch_2cta(const GemmProblem& p, int BN, cudaStream_t st, bool 
     g.stream_k = 1; g.splits = 1; g.kb_per_split = g.kb_total;
     MAGB_REQUIRE((long long)g.tiles_m * g.tiles_n * g.kb_total * 128 < (1ll << 31), "gemm: stream-K unit count overflows");
   }
+  CUtensorMap to;
+  rc = output_map(p, ta, &to, &g);
+  if (rc) return rc;
   if (persistent) {
-    if (BN == 256) return launch2p_majors<256, 4, 8>(p.a_mn, p.b_mn, ta, tb, g, st);
-    return launch2p_majors<128, 6, 8>(p.a_mn, p.b_mn, ta, tb, g, st);
+    if (BN == 256) return launch2p_majors<256, 4, 8>(p.a_mn, p.b_mn, ta, tb, to, g, st);
+    return launch2p_majors<128, 6, 8>(p.a_mn, p.b_mn, ta, tb, to, g, st);
   }
   dim3 grid(2 * m_pairs, (p.N + BN - 1) / BN, splits);      // x = M tiles (pair-adjacent), y = N tiles
-  if (BN == 256) return launch2_majors<256, 5>(p.a_mn, p.b_mn, ta, tb, g, grid, st);
-  return launch2_majors<128, 4>(p.a_mn, p.b_mn, ta, tb, g, grid, st);
+  if (BN == 256) return launch2_majors<256, 5>(p.a_mn, p.b_mn, ta, tb, to, g, grid, st);
+  return launch2_majors<128, 4>(p.a_mn, p.b_mn, ta, tb, to, g, grid, st);
 }
 
 int gemm_launch(const GemmProblem& p, cudaStream_t st) {
@@ -273,6 +293,8 @@ int gemm_launch(const GemmProblem& p, cudaStream_t st) {
     if (pol && *pol) g_policy = atoi(pol);
     const char* sk = getenv("MAGB200_STREAMK");
     if (sk && *sk) g_streamk = atoi(sk);
+    const char* tr = getenv("MAGB200_TMA_REDUCE");
+    if (tr && *tr) g_tma_reduce = atoi(tr);
   }
   MAGB_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem %dx%dx%d", p.M, p.N, p.K);
   const bool a32 = p.a_dtype == DT_F32, b32 = p.b_dtype == DT_F32;
@@ -364,17 +386,20 @@ int gemm_launch(const GemmProblem& p, cudaStream_t st) {
     g.drop_scale = 1.0f / (1.0f - p.drop_p);
   }
 
+  CUtensorMap to;
+  rc = output_map(p, ta, &to, &g);
+  if (rc) return rc;
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, splits);
   if (EB == 2) {
-    if (cluster2) return launch_majors<2, 128, 3, 2>(p.a_mn, p.b_mn, ta, tb, g, grid, st);
+    if (cluster2) return launch_majors<2, 128, 3, 2>(p.a_mn, p.b_mn, ta, tb, to, g, grid, st);
     switch (g_cfg) {
-      case 1: return launch_majors<2, 128, 4, 1>(p.a_mn, p.b_mn, ta, tb, g, grid, st);
-      case 3: return launch_majors<2, 256, 3, 1>(p.a_mn, p.b_mn, ta, tb, g, grid, st);
-      case 4: return launch_majors<2, 256, 4, 1>(p.a_mn, p.b_mn, ta, tb, g, grid, st);
-      default: return launch_majors<2, 128, 3, 1>(p.a_mn, p.b_mn, ta, tb, g, grid, st);
+      case 1: return launch_majors<2, 128, 4, 1>(p.a_mn, p.b_mn, ta, tb, to, g, grid, st);
+      case 3: return launch_majors<2, 256, 3, 1>(p.a_mn, p.b_mn, ta, tb, to, g, grid, st);
+      case 4: return launch_majors<2, 256, 4, 1>(p.a_mn, p.b_mn, ta, tb, to, g, grid, st);
+      default: return launch_majors<2, 128, 3, 1>(p.a_mn, p.b_mn, ta, tb, to, g, grid, st);
     }
   }
-  return launch_majors<4, 128, 3, 1>(p.a_mn, p.b_mn, ta, tb, g, grid, st);
+  return launch_majors<4, 128, 3, 1>(p.a_mn, p.b_mn, ta, tb, to, g, grid, st);
 }
 
 }  // namespace magb200

@@ -54,6 +54,7 @@ struct GemmArgs {
   unsigned long long drop_seed;
   const unsigned long long* drop_seed_ptr;
   int tiles_m, tiles_n, splits;   // persistent kernel: pair-tiles along M, tiles along N, K splits
+  int tma_reduce;                 // atomic epilogue: 1 = reduce through the TMA engine (third tensor map = out0), 0 = red.global
   int stream_k;                   // persistent kernel, atomic epilogue only: 1 = the (tile, K block) work units are cut
                                   // into one contiguous, equally long range per cluster (stream-K) instead of whole tiles
   int dbg;   // measurement modes (results are garbage): 1 = MMA issue without waiting for operands,
@@ -76,6 +77,23 @@ __device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, ui
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+// fp32 reduction of a staged [32 rows][32 columns] box into global memory by the TMA engine
+// (cp.reduce.async.bulk.tensor ... .add): the sum happens at L2 and the SM issues ONE instruction per box.  The
+// per-lane red.global.add.v4.f32 it replaces is paced by the LSU at about one LANE per clock whatever the vector
+// width (measured: 9.6 k cycles for a CTA's 128 x 256 fp32 tile = 13.6 B/clk, against ~35 B/clk for plain stores),
+// which made the reduction epilogue -- not the main loop -- the longest phase of the weight-gradient and stream-K
+// GEMMs.  Rows / columns outside the tensor are clipped by the TMA unit, so ragged M needs no predication.
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, int c0, int c1, const void* ssrc) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(ssrc))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the bulk operations of this thread have finished READING shared memory (the staging boxes may be rewritten)
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... have completed (global memory updated): before the CTA exits
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t pack_f16(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -96,7 +114,10 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 template <int BN>
 struct EpiStage {
   static constexpr int PITCH = BN * 4 + 16;        // bytes per staged row (fp32 worst case + bank skew)
-  static constexpr int WARP_BYTES = 32 * PITCH;
+  // one warp's staging region; a multiple of 1024 B so that it can also hold SWIZZLE_128B boxes for the TMA
+  // reduction epilogue (BN / 32 boxes of 32 rows x 128 B)
+  static constexpr int WARP_BYTES = (32 * PITCH + 1023) / 1024 * 1024;
+  static_assert((BN / 32) * 4096 <= WARP_BYTES, "reduction boxes do not fit in the staging region");
 };
 
 // global [rows][rowbytes] (pitch gpitch bytes) -> staging, coalesced.  Eight row-slices are requested before the first
@@ -199,6 +220,14 @@ __device__ __forceinline__ void row_write_f32(uint8_t* row, int c, const float (
 #pragma unroll
   for (int j = 0; j < 8; ++j) d[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 }
+// the same 32 columns into box c of a SWIZZLE_128B staging area ([box][32 rows][128 B], 16-byte chunk j of row r lives at
+// chunk j ^ (r & 7)): the layout the TMA reduction reads, and conflict-free for the row-per-lane writes
+__device__ __forceinline__ void row_write_f32_sw(uint8_t* boxes, int lane, int c, const float (&v)[32]) {
+  uint8_t* row = boxes + c * 4096 + lane * 128;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(row + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
 template <bool BF16>
 __device__ __forceinline__ void row_write_16(uint8_t* row, int c, const float (&v)[32]) {
   uint4* d = reinterpret_cast<uint4*>(row + c * 64);
@@ -227,8 +256,8 @@ __device__ __forceinline__ void epi_dropout(const GemmArgs& g, int m, int n, flo
 // One epilogue warp: rows [m_base, m_base+32) x columns [n0, n0+BN) of the output.  `sbias` = epi_stage_bias() result
 // for these columns.  TMEM is drained two 32-column chunks per wait (both tcgen05.ld in flight together).
 struct EpiCtx {
-  int epi; bool aux32, dual16, live; int ncols, m_row, n0, pass;
-  uint8_t* myrow; const float* sbias;
+  int epi; bool aux32, dual16, live, tma_red; int ncols, m_row, n0, pass, lane;
+  uint8_t* myrow; uint8_t* stg; const float* sbias;
 };
 template <int BN>
 __device__ __forceinline__ void epi_chunk(const GemmArgs& g, const EpiCtx& x, int c, const uint32_t (&r)[32]) {
@@ -249,7 +278,8 @@ __device__ __forceinline__ void epi_chunk(const GemmArgs& g, const EpiCtx& x, in
       row_write_f32(myrow, c, v);
       break;
     case EPI_ATOMIC_F32:
-      row_write_f32(myrow, c, v);
+      if (x.tma_red) row_write_f32_sw(x.stg, x.lane, c, v);
+      else row_write_f32(myrow, c, v);
       break;
     case EPI_RELU_F32:
 #pragma unroll
@@ -314,8 +344,8 @@ __device__ __forceinline__ void epi_chunk(const GemmArgs& g, const EpiCtx& x, in
 }
 
 template <int BN>
-__device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& g, uint32_t tmem_warp, int m_base, int n0,
-                                                   uint8_t* stg, int lane, unsigned long long* tr,
+__device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& g, const CUtensorMap* tmO, uint32_t tmem_warp, int m_base,
+                                                   int n0, uint8_t* stg, int lane, unsigned long long* tr,
                                                    const float* sbias = nullptr) {
   static_assert(BN % 64 == 0, "chunks are drained in pairs");
   constexpr int PITCH = EpiStage<BN>::PITCH;
@@ -326,8 +356,11 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& g, uint32_t t
   x.live = rows > 0 && ncols > 0;
   x.ncols = ncols; x.m_row = m_base + lane; x.n0 = n0;
   x.myrow = stg + lane * PITCH;
+  x.stg = stg; x.lane = lane;
+  x.tma_red = x.epi == EPI_ATOMIC_F32 && g.tma_reduce != 0;    // reduction through the TMA engine (tmO describes out0)
   x.sbias = sbias;
   if (tr) tr[0] = clock64();      // debug stamps: [0] entry, [1] first accumulator chunks in registers, [2] staged, [3] stored
+  bulk_wait_read();               // an earlier reduction epilogue of this warp may still be reading the staging tile
   // -------- auxiliary input through the staging tile (coalesced)
   x.aux32 = (x.epi == EPI_STORE_F32) && g.aux != nullptr;
   const bool aux16 = (x.epi == EPI_DGELU_F16);
@@ -360,7 +393,15 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& g, uint32_t t
     }
     __syncwarp();
     if (tr) tr[2] = clock64();
-    if (x.live) {
+    if (x.live && x.tma_red) {
+      // every lane staged its own row of each box: publish to the async proxy, then one lane hands the boxes over
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        for (int c = 0; c * 32 < ncols; ++c) tma_reduce_add_2d(tmO, n0 + c * 32, m_base, stg + c * 4096);
+        bulk_commit();
+      }
+    } else if (x.live) {
       stage_out(stg, PITCH, reinterpret_cast<uint8_t*>(out) + ((size_t)m_base * g.ldo + n0) * es, (size_t)g.ldo * es,
                 rows, ncols * es, lane, x.epi == EPI_ATOMIC_F32);
       if (x.dual16)
@@ -392,7 +433,8 @@ struct GemmSmem {
 // arrivals, tcgen05.commit multicast).
 template <int EB, bool A_MN, bool B_MN, int BN, int STAGES, int CL>
 __global__ void __launch_bounds__(192, 2)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmO, const GemmArgs g) {
   using T = GemmTile<EB>;
   using SM = GemmSmem<EB, A_MN, B_MN, BN, STAGES>;
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
@@ -420,6 +462,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (g.tma_reduce) tma_prefetch_desc(&tmO);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -556,8 +599,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // the accumulator is complete => every TMA load has landed and every MMA has read its operands:
     // the pipeline stages are idle and serve as this warp's staging tile
     static_assert(4 * EpiStage<BN>::WARP_BYTES <= STAGES * SM::STAGE_BYTES, "staging does not fit in the pipeline smem");
-    gemm_epilogue_warp<BN>(g, tmem_base + ((uint32_t)(q * 32) << 16), m0 + q * 32, n0,
+    gemm_epilogue_warp<BN>(g, &tmO, tmem_base + ((uint32_t)(q * 32) << 16), m0 + q * 32, n0,
                            smem + q * EpiStage<BN>::WARP_BYTES, lane, (tr && threadIdx.x == 64) ? tr + 52 : nullptr, sb);
+    bulk_wait_all();          // reduction epilogue: the bulk engine may still be reading this CTA's shared memory
     if (tr && threadIdx.x == 64) tr[61] = clock64();
   }
   tc_fence_before();
@@ -592,7 +636,8 @@ struct Gemm2Smem {
 
 template <bool A_MN, bool B_MN, int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
-gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmO, const GemmArgs g) {
   using T = GemmTile<2>;
   using SM = Gemm2Smem<BN, STAGES>;
   static_assert(BN == 128 || BN == 256, "BN");
@@ -619,6 +664,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (g.tma_reduce) tma_prefetch_desc(&tmO);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -715,8 +761,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                                       : epi_stage_bias(g, reinterpret_cast<float*>(smem + SM::BIAS_OFFSET) + q * BN, n0, BN, lane);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    gemm_epilogue_warp<BN>(g, tmem_base + ((uint32_t)(q * 32) << 16), m0 + q * 32, n0,
+    gemm_epilogue_warp<BN>(g, &tmO, tmem_base + ((uint32_t)(q * 32) << 16), m0 + q * 32, n0,
                            smem + q * EpiStage<BN>::WARP_BYTES, lane, nullptr, sb);
+    bulk_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -802,7 +849,8 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
 
 template <bool A_MN, bool B_MN, int BN, int STAGES, int NEPI>
 __global__ void __launch_bounds__(64 + 32 * NEPI, 1)
-gemm2p_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+gemm2p_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmO, const GemmArgs g) {
   using T = GemmTile<2>;
   using SM = Gemm2pSmem<BN, STAGES, NEPI>;
   static_assert(BN == 128 || BN == 256, "BN");
@@ -831,6 +879,7 @@ gemm2p_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (g.tma_reduce) tma_prefetch_desc(&tmO);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -974,7 +1023,7 @@ gemm2p_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll 1
       for (int sb = 0; sb < WCOLS / SM::SUB; ++sb) {
         const int col = cg * WCOLS + sb * SM::SUB;
-        gemm_epilogue_warp<SM::SUB>(g, tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + col, m_base, nt * BN + col,
+        gemm_epilogue_warp<SM::SUB>(g, &tmO, tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + col, m_base, nt * BN + col,
                                     stg, lane, (tr && threadIdx.x == 64 && acc_it == 0 && sb < 2) ? tr + 44 + 4 * sb : nullptr,
                                     sbw ? sbw + sb * SM::SUB : nullptr);
       }
@@ -984,6 +1033,7 @@ gemm2p_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       if (lane == 0) mbar_arrive_cluster(empty_remote + buf * 8);
       ++acc_it;
     });
+    bulk_wait_all();
   }
   tc_fence_before();
   __syncthreads();

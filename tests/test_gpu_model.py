@@ -282,12 +282,12 @@ def test_driver_loop_with_the_drop_in_adamw_takes_the_fused_path_and_matches_the
         no_decay = ["bias", "LayerNorm.bias", "LayerNorm.weight"]
         groups = [{"params": [p for n, p in named if not any(nd in n for nd in no_decay)], "weight_decay": 0.01},
                   {"params": [p for n, p in named if any(nd in n for nd in no_decay)], "weight_decay": 0.0}]
-        opt = AdamW(groups, lr=1e-3)
+        opt = AdamW(groups, lr=1e-4)
         if not fused:
             opt._fused_checked = True           # never look for the flat layout
-        sched = get_linear_schedule_with_warmup(opt, num_warmup_steps=1, num_training_steps=10)
+        sched = get_linear_schedule_with_warmup(opt, num_warmup_steps=1, num_training_steps=40)
         losses = []
-        for _ in range(3):
+        for _ in range(8):
             logits = model(b["input_ids"], b["visual"], b["acoustic"], token_type_ids=b["token_type_ids"],
                            attention_mask=b["attention_mask"], labels=None)[0]
             loss = torch.nn.MSELoss()(logits.view(-1), b["labels"].view(-1))
@@ -297,11 +297,11 @@ def test_driver_loop_with_the_drop_in_adamw_takes_the_fused_path_and_matches_the
             sched.step()
             opt.zero_grad()
         torch.cuda.synchronize()
-        assert opt.fused_steps_taken == (3 if fused else 0)
+        assert opt.fused_steps_taken == (8 if fused else 0)
         results[fused] = (losses, model._engine.flat.clone())
     lf, lp = results[True][0], results[False][0]
     assert abs(lf[0] - lp[0]) < 1e-5 and abs(lf[2] - lp[2]) < 2e-3 * max(1.0, abs(lp[2])), (lf, lp)
-    assert lf[2] < lf[0]                                                       # and it learns
+    assert lf[-1] < 0.9 * lf[0], lf                                            # and it learns
     # Adam moves every weight by ~lr per step whatever the gradient's size: compare loosely, like the trainer tests
     assert (results[True][1] - results[False][1]).abs().max().item() < 2.5e-3
 
