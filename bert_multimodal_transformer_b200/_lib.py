@@ -73,6 +73,10 @@ SIGNATURES = {
     "magb200_embed_ln_bwd": (c_int, [c_void_p] * 7 + [c_float, c_float, c_uint64, c_uint32, c_int, c_int, c_int,
                                                       c_float] + [c_void_p] * 6),
     "magb200_mag_pack_weights": (c_int, [c_void_p] * 4 + [c_int, c_int, c_int, c_void_p, c_void_p]),
+    "magb200_embed_mag_scratch_bytes": (c_size_t, [c_int]),
+    "magb200_embed_mag_fwd": (c_int, [c_void_p] * 9 + [c_float, c_float, c_uint64, c_uint32] + [c_int] * 6
+                              + [c_void_p] * 4 + [c_float, c_float, c_float, c_uint32] + [c_void_p] * 4
+                              + [c_size_t, c_void_p, c_void_p, c_void_p]),
     "magb200_mag_fwd_exact": (c_int, [c_void_p] * 10 + [c_float, c_float, c_float, c_uint64, c_uint32, c_int, c_int,
                                                         c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "magb200_mag_fwd": (c_int, [c_void_p] * 7 + [c_float, c_float, c_float, c_uint64, c_uint32, c_int, c_int, c_int,

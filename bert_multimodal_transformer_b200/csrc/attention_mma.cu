@@ -100,6 +100,17 @@ __device__ __forceinline__ void frag_b(const __half* s, int n0, int k0, int g, i
   b[1] = ld32(s + (n0 + g) * PITCH + k0 + 2 * t + 8);
 }
 
+// B fragments for B[k][n] = s[k0 + k][n0 + n] (a [k][n] row-major tile: V as [key][d]) for the two n-tiles n0 and n0 + 8,
+// read with ldmatrix.trans straight from the row-major tile (r[0], r[1]: n-tile n0; r[2], r[3]: n-tile n0 + 8) -- no
+// transposed copy of the tile in shared memory
+__device__ __forceinline__ void frag_b_trans2(const __half* s, int k0, int n0, int lane, uint32_t (&r)[4]) {
+  const int m = lane >> 3, rr = lane & 7;
+  const __half* p = s + (k0 + (m & 1) * 8 + rr) * PITCH + n0 + (m >> 1) * 8;
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+
 __device__ __forceinline__ float mask_add(const int64_t* mrow, int j) {
   return mrow == nullptr ? 0.f : (1.0f - (float)mrow[j]) * -10000.0f;   // bert.py:180-182 (3.0.2 arithmetic)
 }
@@ -158,7 +169,6 @@ __global__ void __launch_bounds__(128) sdpa_fwd_mma_kernel(const __half* __restr
   __shared__ __align__(16) __half sQ[SP * PITCH];
   __shared__ __align__(16) __half sK[SP * PITCH];
   __shared__ __align__(16) __half sV[SP * PITCH];
-  __shared__ __align__(16) __half sVt[D * PITCH];
   __shared__ uint32_t sKeep[SP * SP / 32];
   const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -169,8 +179,6 @@ __global__ void __launch_bounds__(128) sdpa_fwd_mma_kernel(const __half* __restr
   load_tile_async(base + 2 * Hd, ld, S, sV);
   if (thresh != 0) fill_keep_bits(sKeep, seed, site, ((uint64_t)b * heads + h) * S * S, S * S, thresh);
   async_wait_all();
-  __syncthreads();
-  transpose_tile(sV, sVt);
   __syncthreads();
   const int r0 = warp * 16;
   if (r0 >= S) return;
@@ -251,10 +259,11 @@ __global__ void __launch_bounds__(128) sdpa_fwd_mma_kernel(const __half* __restr
     const uint32_t a0 = packh(sc[2 * kk][0], sc[2 * kk][1]), a1 = packh(sc[2 * kk][2], sc[2 * kk][3]);
     const uint32_t a2 = packh(sc[2 * kk + 1][0], sc[2 * kk + 1][1]), a3 = packh(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      uint32_t bb[2];
-      frag_b(sVt, nt * 8, kk * 16, g, t, bb);      // B[k = key][n = d] = Vt[d][key]
-      mma16816(o[nt], a0, a1, a2, a3, bb[0], bb[1]);
+    for (int np = 0; np < 4; ++np) {
+      uint32_t bb[4];
+      frag_b_trans2(sV, kk * 16, np * 16, lane, bb);      // B[k = key][n = d] = V[key][d]
+      mma16816(o[2 * np], a0, a1, a2, a3, bb[0], bb[1]);
+      mma16816(o[2 * np + 1], a0, a1, a2, a3, bb[2], bb[3]);
     }
   }
 #pragma unroll
@@ -486,6 +495,17 @@ __global__ void __launch_bounds__(128) sdpa_bwd_mma_kernel(const __half* __restr
 //            go to shared memory; Pd^T / dS^T reuse the V / dO tiles, which are dead once every warp has left phase 1
 //   phase 2: dV, dK for 16 keys x 32 head dims (dim half hq), reduction over all 64 queries from shared memory
 //   phase 3: dQ for 16 queries (block kb) x 32 head dims
+// shared memory of the 8-warp kernel: transposed operands are read with ldmatrix.trans from the row-major tiles, so no
+// transposed copies exist; Pd^T / dS^T ([key][query]) and dS ([query][key]) have their own tiles
+struct Bwd8Smem {
+  __half q[SP * PITCH], k[SP * PITCH], v[SP * PITCH], dO[SP * PITCH];
+  __half pdT[SP * PITCH], dsT[SP * PITCH], dS[SP * PITCH];
+  float Dq[SP];
+  float lse[SP];
+  float bias[3 * D];
+  uint32_t keep[SP * SP / 32];
+};
+
 template <int NT>
 __device__ __forceinline__ void colsum_part(const float (&acc)[NT][4], float* sacc, int g, int t, bool row0_ok, bool row1_ok) {
 #pragma unroll
@@ -514,7 +534,7 @@ __global__ void __launch_bounds__(256) sdpa_bwd_mma8_kernel(const __half* __rest
   pdl_trigger();   // the next kernel in the stream (a GEMM) may start its private prologue
   const uint64_t seed = seed_in.ptr ? *seed_in.ptr : seed_in.value;
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
+  Bwd8Smem& sm = *reinterpret_cast<Bwd8Smem*>(smem_raw);
   const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int kb = warp & 3, hq = warp >> 2;
@@ -558,10 +578,6 @@ __global__ void __launch_bounds__(256) sdpa_bwd_mma8_kernel(const __half* __rest
     }
   }
   async_wait_all();
-  __syncthreads();
-  transpose_tile(sm.q, sm.qt);
-  transpose_tile(sm.k, sm.kt);
-  transpose_tile(sm.dO, sm.dOt);
   __syncthreads();
   const int64_t* mrow = mask ? mask + (int64_t)b * S : nullptr;
   const int r0 = kb * 16;
@@ -614,9 +630,8 @@ __global__ void __launch_bounds__(256) sdpa_bwd_mma8_kernel(const __half* __rest
       }
     }
   }
-  __syncthreads();                                   // every warp is done reading the V and dO tiles
-  __half* pdT = sm.v;                                // [key][query]
-  __half* dsT = sm.dO;                               // [key][query]
+  __half* pdT = sm.pdT;                              // [key][query]
+  __half* dsT = sm.dsT;                              // [key][query]
   if (active) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -650,12 +665,14 @@ __global__ void __launch_bounds__(256) sdpa_bwd_mma8_kernel(const __half* __rest
       frag_a(pdT, r0, kk * 16, g, t, ap);
       frag_a(dsT, r0, kk * 16, g, t, as);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint32_t bo[2], bq[2];
-        frag_b(sm.dOt, (nb + j) * 8, kk * 16, g, t, bo);     // B[k = query][n = d] = dOt[d][query]
-        frag_b(sm.qt, (nb + j) * 8, kk * 16, g, t, bq);
-        mma16816(dv[j], ap[0], ap[1], ap[2], ap[3], bo[0], bo[1]);
-        mma16816(dk[j], as[0], as[1], as[2], as[3], bq[0], bq[1]);
+      for (int jp = 0; jp < 2; ++jp) {
+        uint32_t bo[4], bq[4];
+        frag_b_trans2(sm.dO, kk * 16, (nb + 2 * jp) * 8, lane, bo);     // B[k = query][n = d] = dO[query][d]
+        frag_b_trans2(sm.q, kk * 16, (nb + 2 * jp) * 8, lane, bq);
+        mma16816(dv[2 * jp], ap[0], ap[1], ap[2], ap[3], bo[0], bo[1]);
+        mma16816(dv[2 * jp + 1], ap[0], ap[1], ap[2], ap[3], bo[2], bo[3]);
+        mma16816(dk[2 * jp], as[0], as[1], as[2], as[3], bq[0], bq[1]);
+        mma16816(dk[2 * jp + 1], as[0], as[1], as[2], as[3], bq[2], bq[3]);
       }
     }
 #pragma unroll
@@ -683,10 +700,11 @@ __global__ void __launch_bounds__(256) sdpa_bwd_mma8_kernel(const __half* __rest
       uint32_t a[4];
       frag_a(sm.dS, r0, kk * 16, g, t, a);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint32_t bb[2];
-        frag_b(sm.kt, (nb + j) * 8, kk * 16, g, t, bb);      // B[k = key][n = d] = Kt[d][key]
-        mma16816(dq[j], a[0], a[1], a[2], a[3], bb[0], bb[1]);
+      for (int jp = 0; jp < 2; ++jp) {
+        uint32_t bb[4];
+        frag_b_trans2(sm.k, kk * 16, (nb + 2 * jp) * 8, lane, bb);      // B[k = key][n = d] = K[key][d]
+        mma16816(dq[2 * jp], a[0], a[1], a[2], a[3], bb[0], bb[1]);
+        mma16816(dq[2 * jp + 1], a[0], a[1], a[2], a[3], bb[2], bb[3]);
       }
     }
 #pragma unroll
@@ -737,7 +755,7 @@ int sdpa_bwd_mma(const __half* qkv, const __half* dctx, const __half* ctx, const
     MAGB_CHECK_CUDA(cudaFuncSetAttribute(sdpa_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(BwdSmem)));
     MAGB_CHECK_CUDA(cudaFuncSetAttribute(sdpa_bwd_mma8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(BwdSmem)));
+                                         (int)sizeof(Bwd8Smem)));
     const char* e = getenv("MAGB200_SDPA_BWD_WARPS");      // 4 = the original one-key-block-per-warp kernel
     four_warps = e && e[0] == '4';
     configured = true;
@@ -746,7 +764,7 @@ int sdpa_bwd_mma(const __half* qkv, const __half* dctx, const __half* ctx, const
     sdpa_bwd_mma_kernel<<<dim3(heads, B), 128, sizeof(BwdSmem), st>>>(qkv, dctx, ctx, lse, mask, S, heads, th, ds, seed,
                                                                      site, oscale, dqkv, dbias);
   else
-    MAGB_CHECK_CUDA(launch_pdl(sdpa_bwd_mma8_kernel, dim3(heads, B), dim3(256), sizeof(BwdSmem), st, qkv, dctx, ctx, lse, mask, S, heads, th, ds, seed,
+    MAGB_CHECK_CUDA(launch_pdl(sdpa_bwd_mma8_kernel, dim3(heads, B), dim3(256), sizeof(Bwd8Smem), st, qkv, dctx, ctx, lse, mask, S, heads, th, ds, seed,
                                                                       site, oscale, dqkv, dbias));
   MAGB_CHECK_CUDA(cudaGetLastError());
   count_launch();

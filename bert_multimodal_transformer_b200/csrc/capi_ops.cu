@@ -65,6 +65,25 @@ int magb200_mag_fwd(const float* text32, const float* visual, const float* acous
                       reinterpret_cast<__half*>(out16), ST);
 }
 
+size_t magb200_embed_mag_scratch_bytes(int T) { return mag_fused_scratch_bytes(T); }
+
+int magb200_embed_mag_fwd(const int64_t* ids, const int64_t* token_type_ids, const float* visual, const float* acoustic,
+                          const float* word, const float* pos, const float* type, const float* emb_gamma,
+                          const float* emb_beta, float emb_eps, float p_emb, uint64_t seed, uint32_t site_emb, int V, int A,
+                          int ka, int T, int S, int vocab, const void* packed16, const float* bias4, const float* mag_gamma,
+                          const float* mag_beta, float beta_shift, float mag_eps, float p_mag, uint32_t site_mag,
+                          float* emb32, void* amag16, float* gates32, void* scratch, size_t scratch_bytes, float* out32,
+                          void* out16, void* stream) {
+  MAGB_REQUIRE(scratch_bytes >= mag_fused_scratch_bytes(T), "embed_mag_fwd: scratch too small (%zu < %zu)", scratch_bytes,
+               mag_fused_scratch_bytes(T));
+  EmbedArgs e;
+  e.ids = ids; e.tt = token_type_ids; e.visual = visual; e.acoustic = acoustic; e.word = word; e.pos = pos; e.type = type;
+  e.gamma = emb_gamma; e.beta = emb_beta; e.eps = emb_eps; e.p = p_emb; e.seed = Seed{seed, nullptr}; e.site = site_emb;
+  e.V = V; e.A = A; e.KA = ka; e.T = T; e.S = S; e.vocab = vocab; e.emb32 = emb32; e.amag = reinterpret_cast<__half*>(amag16);
+  return mag_fused_fwd(e, reinterpret_cast<const __half*>(packed16), bias4, mag_gamma, mag_beta, beta_shift, mag_eps, p_mag,
+                       site_mag, gates32, scratch, out32, reinterpret_cast<__half*>(out16), ST);
+}
+
 int magb200_mag_fwd_exact(const float* text32, const float* visual, const float* acoustic, const float* W_hv,
                           const float* W_ha, const float* W_v, const float* W_a, const float* bias4,
                           const float* ln_gamma, const float* ln_beta, float beta_shift, float ln_eps, float p,

@@ -86,6 +86,11 @@ static int get_tensor_map(CUtensorMap* out, const void* ptr, int dtype, uint64_t
   return 0;
 }
 
+int tensor_map_2d(CUtensorMap* out, const void* ptr, int dtype, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t b0,
+                  uint32_t b1) {
+  return get_tensor_map(out, ptr, dtype, d0, d1, ld, b0, b1);
+}
+
 // Programmatic dependent launch for every GEMM (the kernels call griddepcontrol.wait after their private prologue);
 // MAGB200_PDL=0 turns the attribute off.
 static int pdl_attr(cudaLaunchAttribute* a) {

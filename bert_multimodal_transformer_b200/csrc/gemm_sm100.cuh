@@ -61,6 +61,11 @@ struct GemmArgs {
              // 2 = operand delivery only (no MMA; the consumer releases each stage as soon as it lands)
 };
 
+// cached cuTensorMapEncodeTiled wrapper (gemm.cu): 2-D row-major tensor [d1 rows][d0 contiguous], row pitch ld
+// elements, box [b1][b0] with b0 * element size = 128 B, SWIZZLE_128B
+int tensor_map_2d(CUtensorMap* out, const void* ptr, int dtype, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t b0,
+                  uint32_t b1);
+
 template <int EB>
 struct GemmTile {
   static constexpr int BM = 128;

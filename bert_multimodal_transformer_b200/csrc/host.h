@@ -59,6 +59,12 @@ struct EmbedArgs {
 int embed_ln_fwd(const EmbedArgs& a, cudaStream_t st);
 int embed_ln_bwd(const EmbedArgs& a, const float* dout, float oscale, float* dword, float* dpos, float* dtype,
                  float* dgamma, float* dbeta, cudaStream_t st);
+// mag_fused.cu (K1): embeddings + MAG as one warp-specialised cooperative kernel.  e.emb32 / e.amag are outputs (saved for
+// backward); gates32 [T][3072] may be null (eval); scratch: mag_fused_scratch_bytes(T) bytes
+size_t mag_fused_scratch_bytes(int T);
+int mag_fused_fwd(const EmbedArgs& e, const __half* packed16, const float* bias4, const float* mgamma, const float* mbeta,
+                  float beta_shift, float m_eps, float p_mag, uint32_t site_mag, float* gates32, void* scratch,
+                  float* out32, __half* out16, cudaStream_t st);
 int mag_pack_inputs(const float* text, const float* visual, const float* acoustic, int V, int A, int KA, int T,
                     __half* amag, cudaStream_t st);
 int mag_pack_split(const float* text, const float* visual, const float* acoustic, const float* W_hv, const float* W_ha,

@@ -49,6 +49,7 @@ struct BertWs {
   __half* dqkv16[2]; __half* dG16;
   float* dBmag32; __half* dpool16;
   float* attD;     // [B][heads][S] rowsum(dO * O) of the layer in flight (attention backward for S > 64)
+  void* magscratch;   // K1 (mag_fused.cu): h_m rows + grid-barrier words
   size_t bytes;
 };
 
@@ -93,6 +94,7 @@ BertWs carve_ws(const magb200_bert_dims& d, void* base) {
   w.dBmag32 = c.take<float>((size_t)4 * H * d.ka);
   w.dpool16 = c.take<__half>((size_t)d.batch * H);
   w.attD = c.take<float>((size_t)d.batch * d.heads * d.seq);
+  w.magscratch = c.take<uint8_t>(mag_fused_scratch_bytes((int)T));
   w.bytes = (c.off + 1023) & ~size_t(1023);
   return w;
 }
@@ -144,6 +146,15 @@ SideCtx g_side[MAGB200_MAX_DEVICES];
     int _rc = (expr);        \
     if (_rc) return _rc;     \
   } while (0)
+
+bool fused_mag() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MAGB200_FUSED_MAG");
+    v = (e && *e) ? atoi(e) : 0;
+  }
+  return v != 0;
+}
 
 int streamk_forward() {
   static int v = -1;
@@ -230,12 +241,20 @@ int bert_forward(const magb200_bert_dims& d, const int64_t* off, const float* P,
   e.eps = d.ln_eps; e.p = d.p_hidden; e.seed = sd; e.site = SITE_EMB;
   e.V = d.visual_dim; e.A = d.acoustic_dim; e.KA = d.ka; e.T = T; e.S = S; e.vocab = d.vocab;
   e.emb32 = w.emb32; e.amag = w.amag16;
-  RUN(embed_ln_fwd(e, st));
-  // MAG (modeling.py:25-51): one block GEMM for the four Linears, then the fused tail   bert.py:219
-  RUN(linear_fwd(w.amag16, d.ka, P16 + off[MAGB200_OFF_MAG_PACKED16], T, 4 * H, d.ka, P + off[MAGB200_OFF_MAG_BIAS4],
-                 EPI_STORE_F32, w.G32, nullptr, 4 * H, st, 2 * H, H));
-  RUN(mag_tail_fwd(w.G32, w.emb32, P + off[MAGB200_OFF_MAG_LN_W], P + off[MAGB200_OFF_MAG_LN_B], d.beta_shift,
-                   d.mag_ln_eps, d.p_mag, sd, SITE_MAG, T, w.x32[0], w.x16[0], st));
+  if (fused_mag()) {
+    // K1: embeddings + MAG in one warp-specialised cooperative kernel (mag_fused.cu); the gate pre-activations are
+    // written for the backward pass but not read back
+    RUN(mag_fused_fwd(e, P16 + off[MAGB200_OFF_MAG_PACKED16], P + off[MAGB200_OFF_MAG_BIAS4], P + off[MAGB200_OFF_MAG_LN_W],
+                      P + off[MAGB200_OFF_MAG_LN_B], d.beta_shift, d.mag_ln_eps, d.p_mag, SITE_MAG, w.G32, w.magscratch,
+                      w.x32[0], w.x16[0], st));
+  } else {
+    RUN(embed_ln_fwd(e, st));
+    // MAG (modeling.py:25-51): one block GEMM for the four Linears, then the fused tail   bert.py:219
+    RUN(linear_fwd(w.amag16, d.ka, P16 + off[MAGB200_OFF_MAG_PACKED16], T, 4 * H, d.ka, P + off[MAGB200_OFF_MAG_BIAS4],
+                   EPI_STORE_F32, w.G32, nullptr, 4 * H, st, 2 * H, H));
+    RUN(mag_tail_fwd(w.G32, w.emb32, P + off[MAGB200_OFF_MAG_LN_W], P + off[MAGB200_OFF_MAG_LN_B], d.beta_shift,
+                     d.mag_ln_eps, d.p_mag, sd, SITE_MAG, T, w.x32[0], w.x16[0], st));
+  }
   // BertEncoder                                                                  bert.py:221-229
   // The FFN-output Linear (N = 768, K = 3072) has 30 pair tiles of 48 K blocks for 74 clusters: it can run as a stream-K
   // reduction into a zeroed buffer (red.add epilogue, bias carried by the partial sum that holds K block 0), which the

@@ -89,6 +89,22 @@ int magb200_embed_ln_bwd(const float* dout, const int64_t* ids, const int64_t* t
                          uint32_t site, int T, int S, int vocab, float out_scale, float* dword, float* dpos, float* dtype,
                          float* dgamma, float* dbeta, void* stream);
 
+/* K1 -- BertEmbeddings (bert.py:211-216) and MAG.forward (modeling.py:25-51, called at bert.py:219) as ONE
+ * warp-specialised cooperative kernel: embedding gather + LayerNorm(emb_eps) + dropout(p_emb), the four gate Linears
+ * on tcgen05 (operand A = [h | visual | acoustic] packed in amag16, B = packed16 from magb200_mag_pack_weights), ReLU
+ * gates, h_m, alpha = min(beta_shift |h| / (|h_m| + 1e-6), 1), LayerNorm(mag_eps)(alpha h_m + h), dropout(p_mag).
+ * Outputs: out32 / out16 (optional) [T][768]; emb32 [T][768] and amag16 [T][ka] (both read by the backward pass);
+ * gates32 [T][3072] = the gate pre-activations for magb200_mag_bwd, or NULL to skip them (inference).
+ * scratch: magb200_embed_mag_scratch_bytes(T) bytes.  Same results as magb200_embed_ln_fwd -> magb200_mag_fwd. */
+size_t magb200_embed_mag_scratch_bytes(int T);
+int magb200_embed_mag_fwd(const int64_t* ids, const int64_t* token_type_ids, const float* visual, const float* acoustic,
+                          const float* word, const float* pos, const float* type, const float* emb_gamma,
+                          const float* emb_beta, float emb_eps, float p_emb, uint64_t seed, uint32_t site_emb, int V, int A,
+                          int ka, int T, int S, int vocab, const void* packed16, const float* bias4, const float* mag_gamma,
+                          const float* mag_beta, float beta_shift, float mag_eps, float p_mag, uint32_t site_mag,
+                          float* emb32, void* amag16, float* gates32, void* scratch, size_t scratch_bytes, float* out32,
+                          void* out16, void* stream);
+
 /* MAG.forward (modeling.py:25-51), all of it:
  *   gates GEMM on tcgen05 (the four Linears W_hv, W_ha, W_v, W_a as one block matrix) followed by the
  *   fused tail (ReLU gates, h_m, the two L2 norms, alpha = min(beta*|text|/(|h_m|+1e-6), 1) with the

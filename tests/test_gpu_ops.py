@@ -249,6 +249,70 @@ def test_sdpa_without_mask_and_range_errors():
     assert lib().magb200_sdpa_fwd(L.ptr(qkv), None, B, S, heads, 32, 0.0, 0, 0, L.ptr(ctx), None, stream()) != 0
 
 
+@pytest.mark.parametrize("T,S,p_emb,p_mag,gates", [(2400, 50, 0.0, 0.0, True), (2400, 50, 0.1, 0.5, True), (150, 50, 0.0, 0.0, False),
+                                                 (1, 1, 0.0, 0.0, True), (20000, 500, 0.1, 0.5, True)])
+def test_embed_mag_fused_kernel_equals_the_three_kernel_path(T, S, p_emb, p_mag, gates):
+    """K1 (magb200_embed_mag_fwd: embeddings + MAG as one warp-specialised cooperative kernel) against the path it
+    replaces (magb200_embed_ln_fwd -> magb200_mag_fwd: packed-gate GEMM + tail kernel) on the same inputs, seeds and
+    dropout sites: same fp16 GEMM operands and fp32 accumulation, so only the summation order may differ.  T = 20000
+    needs several tiles per CTA (the persistent tile loop); gates = False is the inference form (no gate tensor)."""
+    g = _g(12)
+    V, A, vocab, KA = 47, 74, 3000, 896
+    ids = torch.randint(0, vocab, (T,), generator=g)
+    tt = torch.randint(0, 2, (T,), generator=g)
+    vis, aco = torch.randn(T, V, generator=g), torch.randn(T, A, generator=g)
+    vis[::7] = 0
+    aco[::7] = 0                                   # rows with no modality signal: h_m == 0 when the biases are zero
+    word = torch.randn(vocab, H, generator=g) * 0.5
+    pos = torch.randn(512, H, generator=g) * 0.1
+    typ = torch.randn(2, H, generator=g) * 0.1
+    eg, eb = 1 + 0.1 * torch.randn(H, generator=g), 0.1 * torch.randn(H, generator=g)
+    mg, mb = 1 + 0.1 * torch.randn(H, generator=g), 0.1 * torch.randn(H, generator=g)
+    W_hv, W_ha = torch.randn(H, V + H, generator=g) * 0.02, torch.randn(H, A + H, generator=g) * 0.02
+    W_v, W_a = torch.randn(H, V, generator=g) * 0.02, torch.randn(H, A, generator=g) * 0.02
+    bias4 = torch.randn(4 * H, generator=g) * 0.02
+    bias4[2 * H:] = 0
+    seed = 4242
+    c = Dev()
+    d = {k: c(v) for k, v in dict(ids=ids, tt=tt, vis=vis, aco=aco, word=word, pos=pos, typ=typ, eg=eg, eb=eb, mg=mg, mb=mb,
+                                  W_hv=W_hv, W_ha=W_ha, W_v=W_v, W_a=W_a, bias4=bias4).items()}
+    packed = torch.empty(4 * H * KA, device="cuda", dtype=torch.float16)
+    L.check(lib().magb200_mag_pack_weights(L.ptr(d["W_hv"]), L.ptr(d["W_ha"]), L.ptr(d["W_v"]), L.ptr(d["W_a"]), V, A, KA,
+                                           L.ptr(packed), stream()))
+    # the three-kernel path
+    emb_a = torch.empty(T, H, device="cuda")
+    amag_a = torch.empty(T, KA, device="cuda", dtype=torch.float16)
+    L.check(lib().magb200_embed_ln_fwd(L.ptr(d["ids"]), L.ptr(d["tt"]), L.ptr(d["vis"]), L.ptr(d["aco"]), L.ptr(d["word"]),
+                                       L.ptr(d["pos"]), L.ptr(d["typ"]), L.ptr(d["eg"]), L.ptr(d["eb"]), 1e-12, p_emb, seed,
+                                       1, V, A, KA, T, S, vocab, L.ptr(emb_a), L.ptr(amag_a), stream()))
+    amag_tmp = torch.empty(T, KA, device="cuda", dtype=torch.float16)
+    gates_a = torch.empty(T, 4 * H, device="cuda")
+    out_a = torch.empty(T, H, device="cuda")
+    L.check(lib().magb200_mag_fwd(L.ptr(emb_a), L.ptr(d["vis"]), L.ptr(d["aco"]), L.ptr(packed), L.ptr(d["bias4"]),
+                                  L.ptr(d["mg"]), L.ptr(d["mb"]), 1.0, 1e-5, p_mag, seed, 2, V, A, KA, T, L.ptr(amag_tmp),
+                                  L.ptr(gates_a), L.ptr(out_a), None, stream()))
+    # K1
+    emb_b = torch.empty(T, H, device="cuda")
+    amag_b = torch.empty(T, KA, device="cuda", dtype=torch.float16)
+    gates_b = torch.full((T, 4 * H), float("nan"), device="cuda") if gates else None
+    out_b = torch.empty(T, H, device="cuda")
+    out16_b = torch.empty(T, H, device="cuda", dtype=torch.float16)
+    nscr = lib().magb200_embed_mag_scratch_bytes(T)
+    scratch = torch.empty(nscr, dtype=torch.uint8, device="cuda")
+    L.check(lib().magb200_embed_mag_fwd(L.ptr(d["ids"]), L.ptr(d["tt"]), L.ptr(d["vis"]), L.ptr(d["aco"]), L.ptr(d["word"]),
+                                        L.ptr(d["pos"]), L.ptr(d["typ"]), L.ptr(d["eg"]), L.ptr(d["eb"]), 1e-12, p_emb, seed, 1,
+                                        V, A, KA, T, S, vocab, L.ptr(packed), L.ptr(d["bias4"]), L.ptr(d["mg"]), L.ptr(d["mb"]),
+                                        1.0, 1e-5, p_mag, 2, L.ptr(emb_b), L.ptr(amag_b), L.ptr(gates_b), L.ptr(scratch), nscr,
+                                        L.ptr(out_b), L.ptr(out16_b), stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(emb_a, emb_b) and torch.equal(amag_a, amag_b)              # phase 1 is the same arithmetic
+    if gates:
+        assert (gates_a - gates_b).abs().max().item() < 1e-4
+    assert (out_a - out_b).abs().max().item() < 2e-4
+    assert (out16_b.float() - out_b).abs().max().item() < 4e-3
+    assert torch.isfinite(out_b).all()
+
+
 @pytest.mark.parametrize("name", ["mag_mosi", "mag_mosi_zero_rows_beta1e-3", "mag_mosei"])
 def test_mag_op_against_reference_golden(golden_dir, name):
     """BASELINE.json configs[0]: MAG(768, V, A) bs=4 seq=50 against outputs of the verbatim reference.
