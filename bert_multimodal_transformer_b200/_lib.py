@@ -85,6 +85,8 @@ SIGNATURES = {
                                                  c_int, c_float] + [c_void_p] * 11),
     "magb200_dropout_residual_ln_fwd": (c_int, [c_void_p] * 4 + [c_float, c_float, c_uint64, c_uint32, c_int]
                                         + [c_void_p] * 4),
+    "magb200_linear_ln_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int] + [c_void_p] * 4
+                              + [c_float, c_float, c_uint64, c_uint32] + [c_void_p] * 4),
     "magb200_ln_bwd": (c_int, [c_void_p] * 5 + [c_float, c_uint64, c_uint32, c_int, c_float] + [c_void_p] * 6),
     "magb200_colsum_f16": (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p]),
     "magb200_sdpa_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_uint64, c_uint32, c_void_p,

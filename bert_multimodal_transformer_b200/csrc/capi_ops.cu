@@ -141,6 +141,16 @@ int magb200_dropout_residual_ln_fwd(const float* pre, const float* res, const fl
                                  ST);
 }
 
+int magb200_linear_ln_fwd(const void* A16, int lda, const void* W16, int M, int K, const float* bias, const float* res,
+                          const float* gamma, const float* beta, float eps, float p, uint64_t seed, uint32_t site, float* y32,
+                          void* y16, float* rstd, void* stream) {
+  GemmLnProblem q;
+  q.A = A16; q.W = W16; q.M = M; q.K = K; q.lda = lda; q.bias = bias; q.res = res; q.gamma = gamma; q.beta = beta; q.eps = eps;
+  q.y32 = y32; q.y16 = reinterpret_cast<__half*>(y16); q.rstd = rstd; q.drop_p = p; q.drop_seed = Seed{seed, nullptr};
+  q.drop_site = site;
+  return gemm_ln_launch(q, ST);
+}
+
 int magb200_ln_bwd(const float* dy32, const float* y32, const float* gamma, const float* beta, const float* rstd,
                    float p, uint64_t seed, uint32_t site, int T, float out_scale, float* dz32, void* dpre16,
                    float* dgamma, float* dbeta, float* dbias, void* stream) {

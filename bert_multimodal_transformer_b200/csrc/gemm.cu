@@ -1,5 +1,6 @@
 // Host side of the tcgen05 GEMM: TMA descriptor construction (cached), kernel selection, launch.
 #include "gemm_sm100.cuh"
+#include "gemm_ln_sm100.cuh"
 #include "host.h"
 
 #include <mutex>
@@ -286,6 +287,51 @@ static int gemm_launch_2cta(const GemmProblem& p, int BN, cudaStream_t st, bool 
   dim3 grid(2 * m_pairs, (p.N + BN - 1) / BN, splits);      // x = M tiles (pair-adjacent), y = N tiles
   if (BN == 256) return launch2_majors<256, 5>(p.a_mn, p.b_mn, ta, tb, to, g, grid, st);
   return launch2_majors<128, 4>(p.a_mn, p.b_mn, ta, tb, to, g, grid, st);
+}
+
+// Linear + dropout + residual + LayerNorm (N = 768) on clusters of 2 x 3 CTAs (gemm_ln_sm100.cuh)
+int gemm_ln_launch(const GemmLnProblem& p, cudaStream_t st) {
+  constexpr int STAGES = 4;
+  using SM = GemmLnSmem<STAGES>;
+  MAGB_REQUIRE(p.M > 0 && p.K > 0 && p.K % 8 == 0 && p.lda % 8 == 0, "gemm_ln: bad shape M=%d K=%d lda=%d", p.M, p.K, p.lda);
+  MAGB_REQUIRE(p.A && p.W && p.bias && p.res && p.gamma && p.beta && p.y32, "gemm_ln: null operand");
+  CUtensorMap ta, tb;
+  int rc = get_tensor_map(&ta, p.A, DT_F16, (uint64_t)p.K, (uint64_t)p.M, (uint64_t)p.lda, 64, 128);
+  if (rc) return rc;
+  rc = get_tensor_map(&tb, p.W, DT_F16, (uint64_t)p.K, (uint64_t)LN_N, (uint64_t)p.K, 64, LN_BN / 2);
+  if (rc) return rc;
+  GemmLnArgs g;
+  g.M = p.M; g.K = p.K; g.kb_total = (p.K + 63) / 64;
+  g.bias = p.bias; g.res = p.res; g.gamma = p.gamma; g.beta = p.beta; g.eps = p.eps;
+  g.y32 = p.y32; g.y16 = p.y16; g.rstd = p.rstd;
+  g.idesc = make_idesc(0u, 0u, false, false, 256, LN_BN);
+  g.drop_thresh = 0; g.drop_scale = 1.f; g.drop_site = p.drop_site; g.drop_seed = p.drop_seed.value;
+  g.drop_seed_ptr = reinterpret_cast<const unsigned long long*>(p.drop_seed.ptr);
+  if (p.drop_p > 0.f) {
+    const double t = (double)p.drop_p * 4294967296.0;
+    g.drop_thresh = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
+    g.drop_scale = 1.0f / (1.0f - p.drop_p);
+  }
+  auto kern = gemm2_ln_tcgen05_kernel<STAGES>;
+  static bool configured[16] = {false};
+  int dev = 0;
+  MAGB_CHECK_CUDA(cudaGetDevice(&dev));
+  MAGB_REQUIRE(dev >= 0 && dev < 16, "gemm_ln: device index %d out of range", dev);
+  if (!configured[dev]) {
+    MAGB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    configured[dev] = true;
+  }
+  const int m_pairs = (p.M + 255) / 256;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * m_pairs, LN_NT, 1); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = SM::TOTAL; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = LN_NT; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1 + pdl_attr(attr + 1);
+  MAGB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, g));
+  MAGB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
 }
 
 int gemm_launch(const GemmProblem& p, cudaStream_t st) {

@@ -39,6 +39,18 @@ struct GemmProblem {
 };
 
 int gemm_launch(const GemmProblem& p, cudaStream_t stream);
+
+// y = LayerNorm(dropout(A W^T + bias) + res), hidden size 768, as one kernel (gemm_ln_sm100.cuh): A [M][K] fp16, W [768][K]
+// fp16 (both K-major), res / y32 [M][768] fp32, y16 (nullable) fp16 copy, rstd (nullable) [M] saved for the backward pass
+struct GemmLnProblem {
+  const void* A = nullptr; const void* W = nullptr;
+  int M = 0, K = 0, lda = 0;
+  const float* bias = nullptr; const float* res = nullptr; const float* gamma = nullptr; const float* beta = nullptr;
+  float eps = 1e-12f;
+  float* y32 = nullptr; __half* y16 = nullptr; float* rstd = nullptr;
+  float drop_p = 0.f; Seed drop_seed; uint32_t drop_site = 0;
+};
+int gemm_ln_launch(const GemmLnProblem& p, cudaStream_t stream);
 void gemm_set_debug(unsigned long long* trace, int cfg);
 
 // ---------------------------------------------------------------- rowops.cu

@@ -147,6 +147,26 @@ SideCtx g_side[MAGB200_MAX_DEVICES];
     if (_rc) return _rc;     \
   } while (0)
 
+// MAGB200_FUSED_LN=1: the attention-output and FFN-output Linears run with dropout + residual + LayerNorm in their
+// epilogue (gemm_ln_sm100.cuh) instead of a GEMM followed by dropout_residual_ln_fwd
+bool fused_ln() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MAGB200_FUSED_LN");
+    v = (e && *e) ? atoi(e) : 0;
+  }
+  return v != 0;
+}
+
+int linear_ln_fwd(const __half* A, int lda, const __half* W, int M, int K, const float* bias, const float* res,
+                  const float* gamma, const float* beta, float eps, float p, Seed sd, uint32_t site, float* y32, __half* y16,
+                  float* rstd, cudaStream_t st) {
+  GemmLnProblem q;
+  q.A = A; q.W = W; q.M = M; q.K = K; q.lda = lda; q.bias = bias; q.res = res; q.gamma = gamma; q.beta = beta; q.eps = eps;
+  q.y32 = y32; q.y16 = y16; q.rstd = rstd; q.drop_p = p; q.drop_seed = sd; q.drop_site = site;
+  return gemm_ln_launch(q, st);
+}
+
 bool fused_mag() {
   static int v = -1;
   if (v < 0) {
@@ -260,6 +280,7 @@ int bert_forward(const magb200_bert_dims& d, const int64_t* off, const float* P,
   // reduction into a zeroed buffer (red.add epilogue, bias carried by the partial sum that holds K block 0), which the
   // LayerNorm kernel that consumes it hands back zeroed.  MAGB200_STREAMK_FWD: 0 = off, 1 = FFN-out, 2 = attention
   // output too (K = 768: 5 K blocks per cluster against a full-tile reduction epilogue -- measured slower).
+  const bool fln = fused_ln();
   const int skf = streamk_forward();
   const int epi_ffn = skf >= 1 ? EPI_ATOMIC_F32 : EPI_STORE_F32, epi_ao = skf >= 2 ? EPI_ATOMIC_F32 : EPI_STORE_F32;
   float* pre_ffn = skf >= 1 ? w.pre32b : w.pre32;       // reduction targets are dedicated, always-zero buffers
@@ -272,17 +293,29 @@ int bert_forward(const magb200_bert_dims& d, const int64_t* off, const float* P,
     RUN(linear_fwd(w.x16[l], H, P16 + o[MAGB200_LOFF_QKV_W], T, 3 * H, H, P + o[MAGB200_LOFF_QKV_B], EPI_STORE_F16,
                    L.qkv16, nullptr, 3 * H, st));
     RUN(sdpa_fwd(L.qkv16, mask, B, S, d.heads, H / d.heads, d.p_attn, sd, site_attn_prob(l), L.ctx16, L.lse, st));
+    if (fln) {
+      RUN(linear_ln_fwd(L.ctx16, H, P16 + o[MAGB200_LOFF_AO_W], T, H, P + o[MAGB200_LOFF_AO_B], w.x32[l],
+                        P + o[MAGB200_LOFF_LN1_W], P + o[MAGB200_LOFF_LN1_B], d.ln_eps, d.p_hidden, sd, site_attn_out(l), L.a32,
+                        L.a16, L.rstd1, st));
+    } else {
     RUN(linear_fwd(L.ctx16, H, P16 + o[MAGB200_LOFF_AO_W], T, H, H, P + o[MAGB200_LOFF_AO_B], epi_ao, pre_ao,
                    nullptr, H, st));
     RUN(dropout_residual_ln_fwd(pre_ao, w.x32[l], P + o[MAGB200_LOFF_LN1_W], P + o[MAGB200_LOFF_LN1_B], d.ln_eps,
                                 d.p_hidden, sd, site_attn_out(l), T, L.a32, L.a16, L.rstd1, st, skf >= 2 ? pre_ao : nullptr));
+    }
     RUN(linear_fwd(L.a16, H, P16 + o[MAGB200_LOFF_F1_W], T, I, H, P + o[MAGB200_LOFF_F1_B], EPI_GELU_F16, L.g16, L.gp16,
                    I, st));
+    if (fln) {
+      RUN(linear_ln_fwd(L.g16, I, P16 + o[MAGB200_LOFF_F2_W], T, I, P + o[MAGB200_LOFF_F2_B], L.a32, P + o[MAGB200_LOFF_LN2_W],
+                        P + o[MAGB200_LOFF_LN2_B], d.ln_eps, d.p_hidden, sd, site_ffn_out(l), w.x32[l + 1], w.x16[l + 1],
+                        L.rstd2, st));
+    } else {
     RUN(linear_fwd(L.g16, I, P16 + o[MAGB200_LOFF_F2_W], T, H, I, P + o[MAGB200_LOFF_F2_B], epi_ffn, pre_ffn,
                    nullptr, H, st));
     RUN(dropout_residual_ln_fwd(pre_ffn, L.a32, P + o[MAGB200_LOFF_LN2_W], P + o[MAGB200_LOFF_LN2_B], d.ln_eps,
                                 d.p_hidden, sd, site_ffn_out(l), T, w.x32[l + 1], w.x16[l + 1], L.rstd2, st,
                                 skf >= 1 ? pre_ffn : nullptr));
+    }
   }
   // BertPooler on the CLS rows (row pitch S*H) + classifier                       bert.py:231, 304-307
   RUN(linear_fwd(w.x16[d.layers], S * H, P16 + off[MAGB200_OFF_POOL_W], B, H, H, P + off[MAGB200_OFF_POOL_B],

@@ -141,6 +141,14 @@ int magb200_mag_bwd(const float* dout, const float* text32, const void* amag16, 
 int magb200_dropout_residual_ln_fwd(const float* pre, const float* res, const float* gamma, const float* beta,
                                     float eps, float p, uint64_t seed, uint32_t site, int T, float* y32, void* y16,
                                     float* rstd, void* stream);
+/* BertSelfOutput / BertOutput as ONE kernel: y = LayerNorm(dropout(A W^T + bias) + res) with hidden size 768 -- the Linear
+ * on tcgen05 (A16 [M][K] pitch lda, W16 [768][K], fp16 K-major) and dropout + residual + LayerNorm in its epilogue
+ * (clusters of 2 x 3 CTAs own 256 rows x 768 columns and exchange the row statistics through distributed shared memory).
+ * Same outputs and dropout mask as magb200_gemm(EPI_STORE_F32) -> magb200_dropout_residual_ln_fwd: y32 [M][768],
+ * y16 (optional) fp16 copy, rstd (optional) [M] for magb200_ln_bwd. */
+int magb200_linear_ln_fwd(const void* A16, int lda, const void* W16, int M, int K, const float* bias, const float* res,
+                          const float* gamma, const float* beta, float eps, float p, uint64_t seed, uint32_t site, float* y32,
+                          void* y16, float* rstd, void* stream);
 /* dz32 = gradient wrt (dropout(pre)+res); dpre16 = fp16 dropout-masked gradient wrt pre; dgamma/dbeta/dbias += */
 int magb200_ln_bwd(const float* dy32, const float* y32, const float* gamma, const float* beta, const float* rstd,
                    float p, uint64_t seed, uint32_t site, int T, float out_scale, float* dz32, void* dpre16,

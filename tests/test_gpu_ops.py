@@ -249,6 +249,44 @@ def test_sdpa_without_mask_and_range_errors():
     assert lib().magb200_sdpa_fwd(L.ptr(qkv), None, B, S, heads, 32, 0.0, 0, 0, L.ptr(ctx), None, stream()) != 0
 
 
+@pytest.mark.parametrize("M,K,p", [(2400, 768, 0.0), (2400, 3072, 0.1), (2400, 768, 0.1), (300, 768, 0.0), (1, 3072, 0.1),
+                                   (16384, 768, 0.1)])
+def test_linear_with_layernorm_epilogue(M, K, p):
+    """magb200_linear_ln_fwd (Linear + dropout + residual + LayerNorm in one tcgen05 kernel, row statistics exchanged
+    across a 2 x 3 cluster) against torch fp32 on the same fp16 operands with the kernels' dropout mask, and against the
+    two-kernel path it replaces (same mask: both use element index m * 768 + n at the same site)."""
+    g = _g(21)
+    A = (torch.randn(M, K, generator=g) * 0.5).half()
+    W = (torch.randn(H, K, generator=g) * 0.05).half()
+    bias = torch.randn(H, generator=g) * 0.1
+    res = torch.randn(M, H, generator=g)
+    gamma, beta = 1 + 0.1 * torch.randn(H, generator=g), 0.1 * torch.randn(H, generator=g)
+    seed, site = 555, 17
+    keep = keep_mask((M, H), p, seed, site).cpu() if p > 0 else torch.ones(M, H)
+    z = (A.float() @ W.float().t() + bias) * keep / (1 - p) + res
+    ref = F.layer_norm(z, (H,), gamma, beta, 1e-12)
+    rstd_ref = 1.0 / torch.sqrt(z.var(dim=1, unbiased=False) + 1e-12)
+    c = Dev()
+    y32 = torch.full((M, H), float("nan"), device="cuda")
+    y16 = torch.zeros(M, H, device="cuda", dtype=torch.float16)
+    rstd = torch.zeros(M, device="cuda")
+    L.check(lib().magb200_linear_ln_fwd(L.ptr(c(A)), K, L.ptr(c(W)), M, K, L.ptr(c(bias)), L.ptr(c(res)), L.ptr(c(gamma)),
+                                        L.ptr(c(beta)), 1e-12, p, seed, site, L.ptr(y32), L.ptr(y16), L.ptr(rstd), stream()))
+    torch.cuda.synchronize()
+    assert (y32.cpu() - ref).abs().max().item() < 2e-3 * math.sqrt(K / 768)
+    assert (y16.float() - y32).abs().max().item() < 4e-3
+    assert ((rstd.cpu() - rstd_ref).abs() / rstd_ref).max().item() < 1e-3
+    # the path it replaces
+    pre = torch.empty(M, H, device="cuda")
+    L.check(lib().magb200_gemm(L.ptr(c.keep[0]), L.ptr(c.keep[1]), M, H, K, K, K, L.F16, L.F16, 0, 0, L.EPI_STORE_F32,
+                               L.ptr(c.keep[2]), L.ptr(pre), None, None, H, 1.0, 1, 0, 0, stream()))
+    y32b = torch.empty(M, H, device="cuda")
+    L.check(lib().magb200_dropout_residual_ln_fwd(L.ptr(pre), L.ptr(c.keep[3]), L.ptr(c.keep[4]), L.ptr(c.keep[5]), 1e-12, p,
+                                                  seed, site, M, L.ptr(y32b), None, None, stream()))
+    torch.cuda.synchronize()
+    assert (y32 - y32b).abs().max().item() < 1e-4
+
+
 @pytest.mark.parametrize("T,S,p_emb,p_mag,gates", [(2400, 50, 0.0, 0.0, True), (2400, 50, 0.1, 0.5, True), (150, 50, 0.0, 0.0, False),
                                                  (1, 1, 0.0, 0.0, True), (20000, 500, 0.1, 0.5, True)])
 def test_embed_mag_fused_kernel_equals_the_three_kernel_path(T, S, p_emb, p_mag, gates):
