@@ -113,6 +113,7 @@ SIGNATURES = {
     "magb200_bert_backward_adamw": (c_int, [POINTER(BertDims), POINTER(c_int64)] + [c_void_p] * 6 +
                                     [c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float,
                                      c_float, c_float, c_int, c_float, c_int, c_void_p, c_void_p]),
+    "magb200_bert_attention_probs": (c_int, [POINTER(BertDims), c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "magb200_bert_peek": (c_int, [POINTER(BertDims), c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "magb200_xlnet_workspace_bytes": (c_size_t, [POINTER(XlnetDims)]),
     "magb200_xlnet_refresh_operands": (c_int, [POINTER(XlnetDims), POINTER(c_int64), c_void_p, c_void_p, c_void_p]),

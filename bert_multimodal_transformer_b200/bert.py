@@ -241,9 +241,6 @@ class MAG_BertForSequenceClassification(nn.Module):
             raise ValueError("You have to specify either input_ids or inputs_embeds")
         if inputs_embeds is not None or position_ids is not None or head_mask is not None:
             raise NotImplementedError("inputs_embeds / position_ids / head_mask are not supported by the native path")
-        if output_attentions or output_hidden_states or getattr(self.config, "output_attentions", False) \
-                or getattr(self.config, "output_hidden_states", False):
-            raise NotImplementedError("output_attentions / output_hidden_states are not materialised by the fused kernels")
         self._ensure_bound()
         eng = self._engine
         dev = eng.flat.device
@@ -265,19 +262,46 @@ class MAG_BertForSequenceClassification(nn.Module):
         params = self._param_list if need_grad else []
         return _MagBertFunction.apply(self, ids, tt, mask, vis, aco, training, need_grad, *params)
 
-    def _encode(self, *args):
-        logits = self._run(*args)
+    def _extras(self, attention_mask, output_attentions, output_hidden_states):
+        """The optional tail of the reference's output tuple (bert.py:122-124, 233-237; transformers 3.0.2 BertEncoder):
+        hidden_states = (MAG output, layer 1 .. L outputs), attentions = per-layer probabilities after dropout.  They
+        are detached copies read back from the workspace of the forward that just ran (the fused kernels keep the
+        residual stream there and never materialise the probabilities, which are recomputed on request)."""
+        cfg = self.config
+        if output_attentions is None:
+            output_attentions = getattr(cfg, "output_attentions", False)
+        if output_hidden_states is None:
+            output_hidden_states = getattr(cfg, "output_hidden_states", False)
+        extras = ()
+        if not (output_attentions or output_hidden_states):
+            return extras
+        dims, ws = self._last
+        eng = self._engine
+        with torch.cuda.device(eng.flat.device):
+            if output_hidden_states:
+                extras += ((eng.peek(dims, ws, L.PEEK_MAG),) +
+                           tuple(eng.peek(dims, ws, L.PEEK_LAYER_OUT, l) for l in range(eng.layers)),)
+            if output_attentions:
+                mask = None if attention_mask is None else attention_mask.to(device=eng.flat.device,
+                                                                             dtype=torch.int64).contiguous()
+                extras += (tuple(eng.attention_probs(dims, ws, l, mask) for l in range(eng.layers)),)
+        return extras
+
+    def _encode(self, input_ids, visual, acoustic, attention_mask, token_type_ids, position_ids, head_mask, inputs_embeds,
+                output_attentions, output_hidden_states):
+        self._run(input_ids, visual, acoustic, attention_mask, token_type_ids, position_ids, head_mask, inputs_embeds,
+                  output_attentions, output_hidden_states)
         dims, ws = self._last
         eng = self._engine
         seq = eng.peek(dims, ws, L.PEEK_LAYER_OUT, eng.layers - 1)
         pooled = eng.peek(dims, ws, L.PEEK_POOLED)
-        return (seq, pooled)
+        return (seq, pooled) + self._extras(attention_mask, output_attentions, output_hidden_states)
 
     def forward(self, input_ids, visual, acoustic, attention_mask=None, token_type_ids=None, position_ids=None,
                 head_mask=None, inputs_embeds=None, labels=None, output_attentions=None, output_hidden_states=None):
         logits = self._run(input_ids, visual, acoustic, attention_mask, token_type_ids, position_ids, head_mask,
                            inputs_embeds, output_attentions, output_hidden_states)
-        outputs = (logits,)
+        outputs = (logits,) + self._extras(attention_mask, output_attentions, output_hidden_states)   # bert.py:309
         if labels is not None:                                                  # bert.py:313-322
             if self.num_labels == 1:
                 loss = nn.functional.mse_loss(logits.view(-1), labels.view(-1).to(logits.dtype))

@@ -64,7 +64,8 @@ template <int MAXJ>  // keys per lane = ceil(S / 32) <= MAXJ
 __global__ void __launch_bounds__(AW * 32) sdpa_fwd_kernel(const __half* __restrict__ qkv,
                                                            const int64_t* __restrict__ mask, int S, int heads,
                                                            float scale, uint32_t thresh, float dscale, Seed seed_in,
-                                                           uint32_t site, __half* __restrict__ ctx) {
+                                                           uint32_t site, __half* __restrict__ ctx,
+                                                           float* __restrict__ probs_out) {
   const uint64_t seed = seed_in.ptr ? *seed_in.ptr : seed_in.value;
   extern __shared__ uint8_t smem_att[];
   __half* sK = reinterpret_cast<__half*>(smem_att);
@@ -112,6 +113,7 @@ __global__ void __launch_bounds__(AW * 32) sdpa_fwd_kernel(const __half* __restr
         const uint64_t idx = (((uint64_t)b * heads + h) * S + i) * S + j;
         p = keep_prob(seed, site, idx, thresh) ? p * dscale : 0.f;
         prow[j] = p;
+        if (probs_out != nullptr) probs_out[idx] = p;          // output_attentions: the (dropped) probabilities
       }
     }
     __syncwarp();
@@ -122,7 +124,8 @@ __global__ void __launch_bounds__(AW * 32) sdpa_fwd_kernel(const __half* __restr
       o0 = fmaf(p, v.x, o0);
       o1 = fmaf(p, v.y, o1);
     }
-    *reinterpret_cast<__half2*>(ctx + ((int64_t)b * S + i) * Hd + h * DH + 2 * lane) = __floats2half2_rn(o0, o1);
+    if (ctx != nullptr)
+      *reinterpret_cast<__half2*>(ctx + ((int64_t)b * S + i) * Hd + h * DH + 2 * lane) = __floats2half2_rn(o0, o1);
   }
 }
 
@@ -240,7 +243,7 @@ static inline void drop_params(float p, uint32_t& thresh, float& scale) {
 
 template <int MAXJ>
 static int launch_fwd(const __half* qkv, const int64_t* mask, int B, int S, int heads, float p, Seed seed,
-                      uint32_t site, __half* ctx, cudaStream_t st) {
+                      uint32_t site, __half* ctx, cudaStream_t st, float* probs_out = nullptr) {
   uint32_t th; float ds;
   drop_params(p, th, ds);
   const size_t smem = (size_t)3 * S * KP * sizeof(__half) + (size_t)AW * S * sizeof(float);
@@ -250,10 +253,21 @@ static int launch_fwd(const __half* qkv, const int64_t* mask, int B, int S, int 
     MAGB_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  k<<<dim3(heads, B), AW * 32, smem, st>>>(qkv, mask, S, heads, 0.125f, th, ds, seed, site, ctx);
+  k<<<dim3(heads, B), AW * 32, smem, st>>>(qkv, mask, S, heads, 0.125f, th, ds, seed, site, ctx, probs_out);
   MAGB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
+}
+
+// attention probabilities P[b][h][i][j] (after dropout, as BertSelfAttention returns them with output_attentions) from the
+// saved q | k | v activations; not on the training path (the fused kernels never materialise P)
+int sdpa_probs(const __half* qkv, const int64_t* mask, int B, int S, int heads, float p, Seed seed, uint32_t site,
+               float* probs, cudaStream_t st) {
+  MAGB_REQUIRE(S >= 1 && S <= 512 && probs != nullptr, "sdpa_probs: bad arguments (S=%d)", S);
+  if (S <= 64) return launch_fwd<2>(qkv, mask, B, S, heads, p, seed, site, nullptr, st, probs);
+  if (S <= 128) return launch_fwd<4>(qkv, mask, B, S, heads, p, seed, site, nullptr, st, probs);
+  if (S <= 256) return launch_fwd<8>(qkv, mask, B, S, heads, p, seed, site, nullptr, st, probs);
+  return launch_fwd<16>(qkv, mask, B, S, heads, p, seed, site, nullptr, st, probs);
 }
 
 int sdpa_fwd(const __half* qkv, const int64_t* mask, int B, int S, int heads, int head_dim, float p, Seed seed,

@@ -252,6 +252,11 @@ int magb200_bert_backward_adamw(const magb200_bert_dims* dims, const int64_t* of
                             &h);
 }
 
+int magb200_bert_attention_probs(const magb200_bert_dims* dims, void* workspace, int layer, const int64_t* attention_mask,
+                                 float* out, size_t out_bytes, void* stream) {
+  return bert_attention_probs(*dims, workspace, layer, attention_mask, out, out_bytes, ST);
+}
+
 int magb200_bert_peek(const magb200_bert_dims* dims, void* workspace, int what, int layer, void* out, size_t out_bytes,
                       void* stream) {
   return bert_peek(*dims, workspace, what, layer, out, out_bytes, ST);

@@ -119,6 +119,8 @@ int sdpa_fwd_flash(const __half* qkv, const int64_t* mask, int B, int S, int hea
                    __half* ctx, float* lse, cudaStream_t st);
 int sdpa_bwd_flash(const __half* qkv, const __half* dctx, const __half* ctx, const float* lse, const int64_t* mask, int B,
                    int S, int heads, float p, Seed seed, uint32_t site, float* Dq_scratch, __half* dqkv, cudaStream_t st);
+int sdpa_probs(const __half* qkv, const int64_t* mask, int B, int S, int heads, float p, Seed seed, uint32_t site,
+               float* probs, cudaStream_t st);
 int sdpa_fwd_mma(const __half* qkv, const int64_t* mask, int B, int S, int heads, float p, Seed seed, uint32_t site,
                  __half* ctx, float* lse, cudaStream_t st);
 int sdpa_bwd_mma(const __half* qkv, const __half* dctx, const __half* ctx, const float* lse, const int64_t* mask, int B,
@@ -188,6 +190,9 @@ int bert_backward_part(const magb200_bert_dims& d, const int64_t* off, const flo
                        const OptHook* opt = nullptr);
 int bert_peek(const magb200_bert_dims& d, void* workspace, int what, int layer, void* out, size_t out_bytes,
               cudaStream_t st);
+// attention probabilities of `layer` ([B][heads][S][S] fp32, after dropout) recomputed from the workspace of a forward
+int bert_attention_probs(const magb200_bert_dims& d, void* workspace, int layer, const int64_t* mask, float* out,
+                         size_t out_bytes, cudaStream_t st);
 }  // namespace magb200
 
 // ---------------------------------------------------------------- model_xlnet.cu

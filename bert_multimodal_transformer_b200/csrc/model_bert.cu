@@ -492,6 +492,17 @@ int bert_backward_part(const magb200_bert_dims& d, const int64_t* off, const flo
   return 0;
 }
 
+int bert_attention_probs(const magb200_bert_dims& d, void* workspace, int layer, const int64_t* mask, float* out,
+                         size_t out_bytes, cudaStream_t st) {
+  RUN(check_dims(d));
+  MAGB_REQUIRE(layer >= 0 && layer < d.layers, "attention_probs: bad layer %d", layer);
+  BertWs w = carve_ws(d, workspace);
+  const size_t n = (size_t)d.batch * d.heads * d.seq * d.seq * sizeof(float);
+  MAGB_REQUIRE(out_bytes >= n, "attention_probs: output buffer too small (%zu < %zu)", out_bytes, n);
+  return sdpa_probs(w.layer[layer].qkv16, mask, d.batch, d.seq, d.heads, d.p_attn, Seed{d.seed, d.seed_dev},
+                    site_attn_prob(layer), out, st);
+}
+
 // Intermediate activations for tests (copies device->device into caller buffers; null = skip)
 int bert_peek(const magb200_bert_dims& d, void* workspace, int what, int layer, void* out, size_t out_bytes,
               cudaStream_t st) {

@@ -203,6 +203,12 @@ class BertEngine:
             else self.offsets[L.OFF_POOL_W]
         return int(start), int(end)
 
+    def attention_probs(self, dims, ws, layer, mask):
+        out = torch.empty(dims.batch, self.heads, dims.seq, dims.seq, dtype=torch.float32, device=self.flat.device)
+        L.check(L.load().magb200_bert_attention_probs(byref(dims), L.ptr(ws), layer, L.ptr(mask), L.ptr(out), out.numel() * 4,
+                                                      L.current_stream()))
+        return out
+
     def peek(self, dims, ws, what, layer=0):
         lib = L.load()
         T = dims.batch * dims.seq

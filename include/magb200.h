@@ -261,6 +261,11 @@ int magb200_bert_backward_adamw(const magb200_bert_dims* dims, const int64_t* of
                                 float* exp_avg, float* exp_avg_sq, const uint8_t* decay_chunk, float lr, float beta1,
                                 float beta2, float eps, float weight_decay, int step, float grad_unscale, int zero_grad,
                                 const float* hyper_dev, void* stream);
+/* output_attentions (bert.py:122-124, 233-237): the attention probabilities of one layer, [B][heads][S][S] fp32 after
+ * dropout, recomputed from the q|k|v activations a forward left in `workspace` (the fused attention kernels never
+ * materialise them). */
+int magb200_bert_attention_probs(const magb200_bert_dims* dims, void* workspace, int layer, const int64_t* attention_mask,
+                                 float* out, size_t out_bytes, void* stream);
 /* copy a saved activation out of the workspace (tests): MAGB200_PEEK_* */
 int magb200_bert_peek(const magb200_bert_dims* dims, void* workspace, int what, int layer, void* out, size_t out_bytes,
                       void* stream);

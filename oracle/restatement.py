@@ -91,6 +91,8 @@ def bert_layer(sd, i, x, ext_mask, n_head, drop=_identity, eps=1e-12, want=None)
     v = heads(F.linear(x, sd[p + "attention.self.value.weight"], sd[p + "attention.self.value.bias"]))
     s = torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(d) + ext_mask
     pr = drop(f"L{i}.attn_prob", F.softmax(s, dim=-1))
+    if want is not None:
+        want[f"L{i}.probs"] = pr                     # what BertSelfAttention returns with output_attentions
     ctx = torch.matmul(pr, v).permute(0, 2, 1, 3).reshape(B, S, H)
     a = F.linear(ctx, sd[p + "attention.output.dense.weight"], sd[p + "attention.output.dense.bias"])
     a = F.layer_norm(drop(f"L{i}.attn_out", a) + x, (H,), sd[p + "attention.output.LayerNorm.weight"],

@@ -182,7 +182,7 @@ def test_api_contract_and_errors():
     with pytest.raises(ValueError, match="cannot specify both"):
         model(cb["input_ids"], cb["visual"], cb["acoustic"], inputs_embeds=torch.zeros(2, 50, 768))
     with pytest.raises(NotImplementedError):
-        model(cb["input_ids"], cb["visual"], cb["acoustic"], output_attentions=True)
+        model(cb["input_ids"], cb["visual"], cb["acoustic"], head_mask=torch.ones(1, 12))
     with torch.no_grad():
         a = model(cb["input_ids"], cb["visual"], cb["acoustic"])[0]                       # default mask / segments
         ones = torch.ones_like(cb["input_ids"])
@@ -332,3 +332,36 @@ def test_long_sequences_forward_backward_match_the_oracle():
             if e > 3e-2:
                 bad.append((k, e))
         assert not bad, (S, bad[:5])
+
+
+def test_output_hidden_states_and_attentions_match_the_oracle():
+    """bert.py:122-124, 233-237 / 309: the optional tail of the output tuple -- (MAG output, every layer's output) and
+    the per-layer attention probabilities -- against the oracle's intermediates."""
+    layers = 2
+    model, sd = make_model(layers, seed=5)
+    model.eval()
+    b = gen.bert_batch(3, 50, seed=13)
+    cb = to_cuda(b)
+    with torch.no_grad():
+        out = model(cb["input_ids"], cb["visual"], cb["acoustic"], attention_mask=cb["attention_mask"],
+                    token_type_ids=cb["token_type_ids"], output_hidden_states=True, output_attentions=True)
+        seq, pooled, hs2, at2 = model.bert(cb["input_ids"], cb["visual"], cb["acoustic"], attention_mask=cb["attention_mask"],
+                                           token_type_ids=cb["token_type_ids"], output_hidden_states=True,
+                                           output_attentions=True)
+    logits, hidden, attn = out
+    assert len(hidden) == layers + 1 and len(attn) == layers and len(hs2) == layers + 1 and len(at2) == layers
+    want = {}
+    ref = R.mag_bert_forward(sd, b["input_ids"], b["visual"], b["acoustic"], b["attention_mask"], b["token_type_ids"],
+                             n_layer=layers, want=want)
+    assert (logits.cpu() - ref).abs().max().item() < LOGIT_TOL
+    assert torch.equal(hidden[-1], seq)
+    assert (hidden[0].cpu() - want["mag"]).abs().max().item() < 5e-3
+    for l in range(layers):
+        assert (hidden[l + 1].cpu() - want[f"L{l}.out"]).abs().max().item() < 2e-2
+        p = attn[l]
+        assert p.shape == (3, 12, 50, 50)
+        assert (p.sum(-1) - 1).abs().max().item() < 1e-4                          # rows of a softmax
+        pad = (cb["attention_mask"] == 0)[:, None, None, :].expand_as(p)
+        assert p[pad].abs().max().item() < 1e-6                                   # masked keys get no probability
+        if f"L{l}.probs" in want:
+            assert (p.cpu() - want[f"L{l}.probs"]).abs().max().item() < 2e-3
