@@ -248,7 +248,8 @@ static int launch_fwd(const __half* qkv, const int64_t* mask, int B, int S, int 
   drop_params(p, th, ds);
   const size_t smem = (size_t)3 * S * KP * sizeof(__half) + (size_t)AW * S * sizeof(float);
   auto k = sdpa_fwd_kernel<MAXJ>;
-  static size_t configured = 0;
+  static size_t configured_by_dev[kMaxDevices] = {0};
+  size_t& configured = configured_by_dev[current_device_slot()];
   if (smem > configured) {
     MAGB_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
@@ -292,7 +293,8 @@ static int launch_bwd(const __half* qkv, const __half* dctx, const int64_t* mask
   const size_t smem = (size_t)3 * S * KP * sizeof(__half) + (size_t)S * (DH + 1) * sizeof(float) +
                       (size_t)2 * S * (S + 1) * sizeof(float);
   auto k = sdpa_bwd_kernel<MAXJ>;
-  static size_t configured = 0;
+  static size_t configured_by_dev[kMaxDevices] = {0};
+  size_t& configured = configured_by_dev[current_device_slot()];
   if (smem > configured) {
     MAGB_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;

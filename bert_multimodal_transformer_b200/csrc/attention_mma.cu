@@ -749,8 +749,9 @@ int sdpa_bwd_mma(const __half* qkv, const __half* dctx, const __half* ctx, const
   MAGB_REQUIRE(S >= 1 && S <= SP, "sdpa_bwd_mma: S=%d out of range", S);
   uint32_t th; float ds;
   drop_params(p, th, ds);
-  static bool configured = false;
+  static bool configured_by_dev[kMaxDevices] = {false};
   static bool four_warps = false;
+  bool& configured = configured_by_dev[current_device_slot()];
   if (!configured) {
     MAGB_CHECK_CUDA(cudaFuncSetAttribute(sdpa_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(BwdSmem)));

@@ -50,6 +50,14 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+// cudaFuncSetAttribute is per device: "configured" flags are kept per device index (one process may drive several GPUs)
+constexpr int kMaxDevices = 16;
+inline int current_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+  return dev;
+}
+
 // ----------------------------------------------------------------------------------------
 // element type tags shared between host API and kernels
 enum DType : int { DT_F32 = 0, DT_F16 = 1, DT_BF16 = 2 };

@@ -106,10 +106,11 @@ static int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const CU
                           cudaStream_t st) {
   using SM = GemmSmem<EB, A_MN, B_MN, BN, STAGES>;
   auto kern = gemm_tcgen05_kernel<EB, A_MN, B_MN, BN, STAGES, CL>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {false};
+  const int dev = current_device_slot();
+  if (!configured[dev]) {
     MAGB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
-    configured = true;
+    configured[dev] = true;
   }
   {
     cudaLaunchConfig_t cfg = {};
@@ -156,10 +157,11 @@ static int launch2_variant(const CUtensorMap& ta, const CUtensorMap& tb, const C
                            cudaStream_t st) {
   using SM = Gemm2Smem<BN, STAGES>;
   auto kern = gemm2_tcgen05_kernel<A_MN, B_MN, BN, STAGES>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {false};
+  const int dev = current_device_slot();
+  if (!configured[dev]) {
     MAGB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
-    configured = true;
+    configured[dev] = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = SM::TOTAL; cfg.stream = st;

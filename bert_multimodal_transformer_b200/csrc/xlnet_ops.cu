@@ -521,7 +521,8 @@ int xl_rel_attn_fwd(const RelAttnArgs& a, __half* ctx, cudaStream_t st) {
   drop_params(a.p, th, ds);
   const size_t smem = rel_common_bytes(a.S) + (size_t)(AW * 64 * 2 + AW * 2 + AW * a.S) * 4;
   auto k = rel_attn_fwd_kernel<2>;
-  static size_t configured = 0;
+  static size_t configured_by_dev[kMaxDevices] = {0};
+  size_t& configured = configured_by_dev[current_device_slot()];
   if (smem > configured) {
     MAGB_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
@@ -543,7 +544,8 @@ int xl_rel_attn_bwd(const RelAttnArgs& a, const __half* dctx, float oscale, __ha
   const size_t smem = rel_common_bytes(S) +
                       (size_t)(S * 65 + 2 * S * (S + 1) + S * 2 + AW * 64 * 2 + AW * 2 + 5 * 64) * 4;
   auto k = rel_attn_bwd_kernel<2>;
-  static size_t configured = 0;
+  static size_t configured_by_dev[kMaxDevices] = {0};
+  size_t& configured = configured_by_dev[current_device_slot()];
   if (smem > configured) {
     MAGB_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
