@@ -36,7 +36,8 @@ constexpr int STAGES = 2;
 constexpr int STG_PITCH = 32 * 4 + 16;  // staging row: 32 fp32 + bank skew
 constexpr int STG_WARP = 32 * STG_PITCH;
 constexpr int SMEM_STG = STAGES * STAGE_BYTES;
-constexpr int SMEM_BAR = SMEM_STG + 4 * STG_WARP;
+constexpr int SMEM_BIAS = SMEM_STG + 4 * STG_WARP;            // bias of the tile's 4 x 128 gate columns (per epilogue warp)
+constexpr int SMEM_BAR = SMEM_BIAS + 4 * 4 * CW * 4;
 constexpr int SMEM_TOTAL = SMEM_BAR + 128 + 1024;
 
 struct MagFusedArgs {
@@ -220,6 +221,11 @@ mag_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int m0 = (tile / a.ntiles) * BM, c0 = (tile % a.ntiles) * CW;
         const int m_base = m0 + q * 32;
         const int rows = min(32, a.T - m_base);
+        // this warp's copy of the tile's biases: [gate][128 columns], staged before the accumulator wait
+        float* sb = reinterpret_cast<float*>(smem + SMEM_BIAS) + q * 4 * CW;
+        for (int i = lane * 4; i < 4 * CW; i += 128)
+          *reinterpret_cast<float4*>(sb + i) = __ldg(reinterpret_cast<const float4*>(a.bias4 + (i / CW) * H + c0 + (i % CW)));
+        __syncwarp();
         mbar_wait(tmem_full_bar, (uint32_t)(n & 1));
         tc_fence_after();
 #pragma unroll 1
@@ -233,8 +239,8 @@ mag_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float gv = __uint_as_float(r0[j]) + __ldg(a.bias4 + col + j);
-            const float pv = __uint_as_float(r1[j]) + __ldg(a.bias4 + 2 * H + col + j);
+            const float gv = __uint_as_float(r0[j]) + sb[c * 32 + j];               // same address in every lane: broadcast
+            const float pv = __uint_as_float(r1[j]) + sb[2 * CW + c * 32 + j];
             r0[j] = __float_as_uint(gv);
             r1[j] = __float_as_uint(pv);
             hm[j] = fmaxf(gv, 0.f) * pv;
@@ -262,8 +268,8 @@ mag_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float ga = __uint_as_float(r0[j]) + __ldg(a.bias4 + H + col + j);
-            const float pa = __uint_as_float(r1[j]) + __ldg(a.bias4 + 3 * H + col + j);
+            const float ga = __uint_as_float(r0[j]) + sb[CW + c * 32 + j];
+            const float pa = __uint_as_float(r1[j]) + sb[3 * CW + c * 32 + j];
             r0[j] = __float_as_uint(ga);
             r1[j] = __float_as_uint(pa);
             hm[j] = fmaf(fmaxf(ga, 0.f), pa, hm[j]);                                  // modeling.py:27-30
