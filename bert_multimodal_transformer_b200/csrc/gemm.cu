@@ -302,6 +302,9 @@ int gemm_ln_launch(const GemmLnProblem& p, cudaStream_t st) {
   if (rc) return rc;
   rc = get_tensor_map(&tb, p.W, DT_F16, (uint64_t)p.K, (uint64_t)LN_N, (uint64_t)p.K, 64, LN_BN / 2);
   if (rc) return rc;
+  CUtensorMap tr;   // residual [M][768] fp32, boxes of 32 rows x 32 columns
+  rc = get_tensor_map(&tr, p.res, DT_F32, (uint64_t)LN_N, (uint64_t)p.M, (uint64_t)LN_N, 32, 32);
+  if (rc) return rc;
   GemmLnArgs g;
   g.M = p.M; g.K = p.K; g.kb_total = (p.K + 63) / 64;
   g.bias = p.bias; g.res = p.res; g.gamma = p.gamma; g.beta = p.beta; g.eps = p.eps;
@@ -330,7 +333,7 @@ int gemm_ln_launch(const GemmLnProblem& p, cudaStream_t st) {
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = LN_NT; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1 + pdl_attr(attr + 1);
-  MAGB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, g));
+  MAGB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tr, g));
   MAGB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

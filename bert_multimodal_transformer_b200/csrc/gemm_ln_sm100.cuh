@@ -7,6 +7,8 @@
 // run tcgen05.mma.cta_group::2 on a 256 x 256 tile exactly like gemm2_tcgen05_kernel, the three pairs (cluster y) own
 // the three column tiles, and the row sums travel through distributed shared memory:
 //
+//   (while the last MMAs drain, the TMA producer refills the now idle pipeline stages with the CTA's 128 x 256 fp32
+//    residual tile as SWIZZLE_128B boxes: one load latency in total instead of one per 32-column chunk)
 //   pass 1   v = acc + bias -> dropout -> + residual;  s1 = sum(v) over the CTA's 256 columns;  v goes BACK to TMEM
 //            (tcgen05.st, 256 B/clk) so nothing is recomputed; s1 -> the 3 CTAs of the row group (st.shared::cluster)
 //   barrier  mean = (s1_0 + s1_1 + s1_2) / 768
@@ -51,8 +53,10 @@ struct GemmLnSmem {
   static constexpr int TOTAL = RED_OFFSET + 2 * LN_NT * 128 * 4 + 1024;
   static constexpr int STG_PITCH = 32 * 4 + 16;                   // staging row: one 32-column fp32 chunk + bank skew
   static constexpr int STG_WARP = 32 * STG_PITCH;
+  static constexpr int RES_BYTES = 4 * (LN_BN / 32) * 4096;       // residual tile: [4 warps][8 chunks] boxes of 32 x 32 fp32
   static_assert(4 * STG_WARP <= STAGES * STAGE_BYTES, "staging does not fit in the pipeline smem");
-  static_assert((2 * STAGES + 1) * 8 + 4 <= 128, "barrier area");
+  static_assert(RES_BYTES <= STAGES * STAGE_BYTES, "the residual tile is staged in the pipeline smem");
+  static_assert((2 * STAGES + 2) * 8 + 4 <= 128, "barrier area");
 };
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -79,7 +83,8 @@ __device__ __forceinline__ void tc_commit_2sm_mask(uint64_t* bar, uint16_t mask)
 
 template <int STAGES>
 __global__ void __launch_bounds__(192, 1)
-gemm2_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmLnArgs g) {
+gemm2_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const __grid_constant__ CUtensorMap tmR, const GemmLnArgs g) {
   using T = GemmTile<2>;
   using SM = GemmLnSmem<STAGES>;
   constexpr int BN = LN_BN;
@@ -89,7 +94,8 @@ gemm2_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFFSET);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* res_bar = tmem_full_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
   float* s_bias = reinterpret_cast<float*>(smem + SM::PAR_OFFSET);
   float* s_gamma = s_bias + BN;
   float* s_beta = s_gamma + BN;
@@ -110,6 +116,7 @@ gemm2_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmR);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -118,6 +125,7 @@ gemm2_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         mbar_init(&empty_bar[s], 1);
       }
       mbar_init(tmem_full_bar, 1);
+      mbar_init(res_bar, 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -153,6 +161,19 @@ gemm2_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         }
       }
     }
+    // every stage has been read by its last MMA -> the pipeline smem is idle: fetch the residual tile into it,
+    // box (q, c) = rows m0 + 32 q .., columns n0 + 32 c .. at offset (8 q + c) * 4096 (rows beyond M are zero-filled)
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      const int uses = (num_kb - s + STAGES - 1) / STAGES;          // how often stage s was filled
+      if (uses > 0) mbar_wait(&empty_bar[s], (uint32_t)((uses - 1) & 1));
+    }
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(res_bar, SM::RES_BYTES);
+      for (int b = 0; b < 4 * (BN / 32); ++b)
+        tma_load_2d(smem + b * 4096, &tmR, res_bar, n0 + (b & 7) * 32, m0 + (b >> 3) * 32);
+    }
+    __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (pair leaders; one lane issues)
     if (leader) {
@@ -204,14 +225,11 @@ gemm2_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     asm volatile("bar.sync 1, 128;" ::: "memory");           // the four epilogue warps
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    mbar_wait(res_bar, 0);                                    // the residual tile has landed in the pipeline smem
     // ---- pass 1: v = dropout(acc + bias) + residual, row sum; v back to TMEM
     float s1 = 0.f;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
-      if (rows > 0)
-        stage_in(stg, SM::STG_PITCH, reinterpret_cast<const uint8_t*>(g.res + (size_t)m_base * LN_N + n0 + c * 32),
-                 (size_t)LN_N * 4, rows, 128, lane);
-      __syncwarp();
       uint32_t r[32];
       tmem_ld_32x32(tw + (uint32_t)(c * 32), r);
       tmem_ld_wait();
@@ -228,11 +246,12 @@ gemm2_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           v[4 * j + 3] = u.w >= g.drop_thresh ? v[4 * j + 3] * g.drop_scale : 0.f;
         }
       }
-      if (lane < rows) {
-        const float4* a4 = reinterpret_cast<const float4*>(myrow);
+      {
+        // residual row of this thread in box (q, c): 16-byte chunk j lives at chunk j ^ (row & 7) (SWIZZLE_128B)
+        const uint8_t* rrow = smem + (q * (BN / 32) + c) * 4096 + lane * 128;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 x = a4[j];
+          const float4 x = *reinterpret_cast<const float4*>(rrow + ((j ^ (lane & 7)) << 4));
           v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
         }
       }
@@ -242,7 +261,6 @@ gemm2_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         r[j] = __float_as_uint(v[j]);
       }
       tmem_st_32x32(tw + (uint32_t)(c * 32), r);
-      __syncwarp();                                    // the staging tile is reloaded in the next iteration
     }
     tmem_st_wait();
     // partial row sum -> the three CTAs that share these rows (same x, y = 0..2)

@@ -39,6 +39,7 @@ class AdamW(Optimizer):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, correct_bias=correct_bias)
         super().__init__(params, defaults)
         self._fused = None          # (engine, exp_avg, exp_avg_sq, decay_chunks) once the flat layout is recognised
+        self._extras = []
         self._fused_checked = False
         self._fused_step = 0
         self.fused_steps_taken = 0
@@ -63,10 +64,14 @@ class AdamW(Optimizer):
         if len(wds) > 1:
             return
         eng = None
-        for g in groups:
+        extras = []       # parameters outside the flat buffer (XLNet's transformer.mask_emb: never used on this path,
+        for g in groups:  # never receives a gradient): they keep the per-tensor path and do not block the fused one
             for p in g["params"]:
                 e = self._engine_of(p)
-                if e is None or (eng is not None and e is not eng):
+                if e is None:
+                    extras.append(p)
+                    continue
+                if eng is not None and e is not eng:
                     return
                 eng = e
         if eng is None or eng.flat is None or not eng.flat.is_cuda:
@@ -74,8 +79,11 @@ class AdamW(Optimizer):
         base, n = eng.flat.data_ptr(), eng.layout.total
         seen = 0
         decay = torch.zeros(n // 256, dtype=torch.uint8)
+        self._extras = extras
         for g in groups:
             for p in g["params"]:
+                if self._engine_of(p) is None:
+                    continue
                 off = (p.data_ptr() - base) // 4
                 if off < 0 or off >= n or off % 256 != 0:
                     return
@@ -96,6 +104,8 @@ class AdamW(Optimizer):
         gbase, pbase = gbuf.data_ptr(), eng.flat.data_ptr()
         for g in self.param_groups:
             for p in g["params"]:
+                if self._engine_of(p) is None:
+                    continue
                 if p.grad is None or p.grad.data_ptr() - gbase != p.data_ptr() - pbase or p.grad.is_sparse:
                     return None
         return gbuf
@@ -123,6 +133,8 @@ class AdamW(Optimizer):
                     eng.after_optimizer_step()
                 eng.operands_dirty = False       # the kernel rewrote the fp16 operand copies
                 self.fused_steps_taken += 1
+                if any(p.grad is not None for p in getattr(self, "_extras", ())):
+                    self._step_per_tensor(only=self._extras)
                 return loss
             if self._fused_step > 0:
                 raise RuntimeError("AdamW: the flat-buffer layout changed after fused steps were taken (model moved or "
@@ -136,10 +148,11 @@ class AdamW(Optimizer):
         return self._bound_flat_ptr
 
     # ------------------------------------------------------------------ general path (transformers 3.0.2, line by line)
-    def _step_per_tensor(self):
+    def _step_per_tensor(self, only=None):
+        chosen = None if only is None else {id(p) for p in only}
         for group in self.param_groups:
             for p in group["params"]:
-                if p.grad is None:
+                if p.grad is None or (chosen is not None and id(p) not in chosen):
                     continue
                 grad = p.grad
                 if grad.is_sparse:
