@@ -139,7 +139,7 @@ def load(path: str | None = None):
     global _lib
     if _lib is not None:
         return _lib
-    path = path or LIB_PATH
+    path = path or os.environ.get("MAGB200_LIB_PATH") or LIB_PATH      # the override serves A/B builds (tools/)
     if not os.path.exists(path):
         raise MagB200Error(
             f"{path} not found: build it with `python -m bert_multimodal_transformer_b200.build` "

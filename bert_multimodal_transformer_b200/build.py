@@ -91,6 +91,29 @@ def build_library(force=False, verbose=False):
     return LIB_PATH
 
 
+def build_variant(out_path, extra_flags):
+    """A second library with extra compile flags (A/B measurements, e.g. -DMAGB200_PHILOX); objects go to a
+    separate directory, the default library and its stamp are untouched.  Select it with MAGB200_LIB_PATH."""
+    nvcc = _find_nvcc()
+    build_dir = os.path.join(CSRC, "build", "variant_" + hashlib.sha256(" ".join(extra_flags).encode()).hexdigest()[:8])
+    os.makedirs(build_dir, exist_ok=True)
+    procs, objs = [], []
+    for src in _sources():
+        obj = os.path.join(build_dir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "-shared"] + list(extra_flags) + ["-c", src, "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{out}")
+    subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out_path] + objs, check=True)
+    return out_path
+
+
 if __name__ == "__main__":
-    path = build_library(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    print(path)
+    if "--philox" in sys.argv:
+        print(build_variant(os.path.join(PKG_DIR, "libmagb200_philox.so"), ["-DMAGB200_PHILOX"]))
+    else:
+        path = build_library(force="--force" in sys.argv, verbose="-v" in sys.argv)
+        print(path)

@@ -358,10 +358,24 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 }
 
 // ---------------------------------------------------------------------------- dropout RNG
-// Counter-based (Philox-4x32-10) so the backward pass regenerates the forward keep-mask from
-// (seed, site, element index) instead of storing it.  One call yields 4 uniform 32-bit words for
-// the 4 consecutive elements starting at index 4*ctr.
-__device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint32_t site, uint64_t ctr) {
+// Counter-based, so the backward pass regenerates the forward keep-mask from (seed, site, element index) instead of
+// storing it: one call yields 4 uniform 32-bit words for the 4 consecutive elements starting at index 4*ctr.
+//
+// Default generator: a keyed integer hash per element -- triple32 (Wellons' hash-prospector: 3 multiplies, avalanche bias
+// 0.02) of (element index ^ k0), xor k1, with (k0, k1) hashed from (seed, site).  ~12 integer ops per element, against
+// ~28 for Philox-4x32-10: ncu showed the row-wise kernels issue-bound ON THE GENERATOR (dropout_residual_ln_fwd: 670
+// warp instructions per row of which ~600 were Philox; ln_bwd about half; the attention kernels a third), so this is a
+// kernel-time matter, not a taste one.  Dropout needs masks that are uniform, independent across elements and sites
+// and reproducible -- not cryptographic quality (tests/test_gpu_ops.py checks rate, determinism and independence).
+// -DMAGB200_PHILOX restores Philox-4x32-10 (the generator torch uses) at every site.
+__device__ __forceinline__ uint32_t hash_triple32(uint32_t x) {
+  x ^= x >> 17; x *= 0xed5ad4bbu;
+  x ^= x >> 11; x *= 0xac4c1b51u;
+  x ^= x >> 15; x *= 0x31848babu;
+  x ^= x >> 14;
+  return x;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint64_t seed, uint32_t site, uint64_t ctr) {
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = site, c3 = 0x2545F491u;
 #pragma unroll
@@ -373,6 +387,19 @@ __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint32_t site, uint64
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
   return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint32_t site, uint64_t ctr) {
+#ifdef MAGB200_PHILOX
+  return philox4x32_10(seed, site, ctr);
+#else
+  // per-(seed, site) keys: loop-invariant at every call site, the compiler hoists them
+  const uint32_t k0 = hash_triple32((uint32_t)seed ^ hash_triple32((uint32_t)(seed >> 32) ^ (site * 0x9E3779B9u + 0x7F4A7C15u)));
+  const uint32_t k1 = hash_triple32(k0 ^ 0x85EBCA6Bu);
+  const uint32_t hi = (uint32_t)(ctr >> 30);                       // element index bits >= 32 (tensors > 4 G elements)
+  const uint32_t base = ((uint32_t)ctr << 2) ^ k0 ^ (hi ? hash_triple32(hi) : 0u);
+  return make_uint4(hash_triple32(base) ^ k1, hash_triple32(base ^ 1u) ^ k1, hash_triple32(base ^ 2u) ^ k1,
+                    hash_triple32(base ^ 3u) ^ k1);
+#endif
 }
 // keep iff u32 >= p * 2^32 ; threshold precomputed on the host side of each kernel
 __device__ __forceinline__ uint32_t dropout_threshold(float p) {

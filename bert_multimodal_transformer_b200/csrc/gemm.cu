@@ -209,8 +209,16 @@ static int launch2p_variant(const CUtensorMap& ta, const CUtensorMap& tb, const 
     MAGB_REQUIRE(n >= 1, "gemm: the persistent 2-CTA kernel does not fit on this device");
     max_clusters[dev] = n < prop.multiProcessorCount / 2 ? n : prop.multiProcessorCount / 2;
   }
-  const int total = g.tiles_m * g.tiles_n * g.splits;
-  const int ncl = total < max_clusters[dev] ? total : max_clusters[dev];
+  // whole-tile scheduling: never more clusters than tiles.  Stream-K: the (tile, K block) units are cut evenly over the
+  // clusters, so every cluster of the device takes part as long as each gets a few K blocks (>= 4: a range boundary
+  // costs a partial-sum epilogue).  (The first stream-K version kept the tile-count bound: the 36-tile weight-gradient
+  // GEMMs ran on 36 of 74 clusters -- profiles/r02_prof_gemm_bwd.raw.csv, grid 72.)
+  long long total = (long long)g.tiles_m * g.tiles_n * g.splits;
+  if (g.stream_k) {
+    total = (long long)g.tiles_m * g.tiles_n * g.kb_total / 4;
+    if (total < 1) total = 1;
+  }
+  const int ncl = total < max_clusters[dev] ? (int)total : max_clusters[dev];
   cfg.gridDim = dim3(2 * ncl, 1, 1);
   MAGB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, g));
   MAGB_CHECK_CUDA(cudaGetLastError());

@@ -388,7 +388,8 @@ __global__ void __launch_bounds__(128) dropout_residual_ln_fwd_kernel(
 //   dz   (fp32)  : gradient wrt the LayerNorm input = gradient of the residual branch
 //   dpre (fp16)  : dropout-masked dz = gradient wrt the GEMM output (operand of dgrad / wgrad GEMMs)
 //   dgamma, dbeta, dbias (+= column sums)
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy32, const float* __restrict__ y32,
+constexpr int LNB_WARPS = 16;
+__global__ void __launch_bounds__(LNB_WARPS * 32, 1) ln_bwd_kernel(const float* __restrict__ dy32, const float* __restrict__ y32,
                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                      const float* __restrict__ rstd_in, uint32_t thresh, float scale,
                                                      Seed seed_in, uint32_t site, int T, float oscale,
@@ -397,39 +398,47 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
                                                      float* __restrict__ dbias) {
   pdl_wait();      // may be launched with the PDL attribute: the predecessor can still be running
   pdl_trigger();   // the next kernel in the stream (a GEMM) may start its private prologue
-  // One block of 8 warps per SM (the three register accumulators cap occupancy anyway); a warp walks rows
-  // t, t + 8*grid, ... with the NEXT row's two loads already in flight while it works on the current one.
+  // One block of 16 warps per SM, (almost) one row per warp: at T = 2400 the kernel is a latency chain per row
+  // (load 6 KB -> two reductions -> store), so rows in flight per SM is what matters.  ncu on the 8-warp version that
+  // kept the three column sums in register accumulators and prefetched the next row: 255 registers, 1 block x 8 warps
+  // per SM, 12 % warps active, 13.8 us.  Here the column sums (dgamma, dbeta, dbias) live in a per-warp shared-memory
+  // slot, so a thread holds two rows at most; the 16 slots are combined once per block.
   const uint64_t seed = seed_in.ptr ? *seed_in.ptr : seed_in.value;
-  __shared__ float red[8 * H];
+  extern __shared__ __align__(16) float lnb_slots[];          // [LNB_WARPS][3][H]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  Row g, b, accg, accb, accp;
+  float* slot = lnb_slots + warp * 3 * H;
+  Row g, b;
   load_row(g, gamma, lane);
   load_row(b, beta, lane);
-  row_zero(accg); row_zero(accb); row_zero(accp);
-  const int stride = gridDim.x * 8;
-  int t = blockIdx.x * 8 + warp;
-  Row dy, xh;
-  float rstd = 0.f;
-  if (t < T) {
+  bool first = true;
+  for (int t = blockIdx.x * LNB_WARPS + warp; t < T; t += gridDim.x * LNB_WARPS) {
+    Row dy, xh;
     load_row(dy, dy32 + (int64_t)t * H, lane);
     load_row(xh, y32 + (int64_t)t * H, lane);
-    rstd = rstd_in[t];
-  }
-  while (t < T) {
-    const int tn = t + stride;
-    Row dyn, xhn;
-    float rstdn = 0.f;
-    if (tn < T) {
-      load_row(dyn, dy32 + (int64_t)tn * H, lane);
-      load_row(xhn, y32 + (int64_t)tn * H, lane);
-      rstdn = rstd_in[tn];
-    }
+    const float rstd = rstd_in[t];
+    Row cg;                       // this row's contribution to dgamma; dbeta's is dy itself
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < 4 * VEC; ++i) {
       xh.v[i] = fabsf(g.v[i]) > 1e-20f ? (xh.v[i] - b.v[i]) / g.v[i] : 0.f;
-      accg.v[i] += dy.v[i] * xh.v[i];
-      accb.v[i] += dy.v[i];
+      cg.v[i] = dy.v[i] * xh.v[i];
+    }
+    if (first) {
+      store_row(cg, slot, lane);
+      store_row(dy, slot + H, lane);
+    } else {
+      Row a;
+      load_row(a, slot, lane);
+#pragma unroll
+      for (int i = 0; i < 4 * VEC; ++i) a.v[i] += cg.v[i];
+      store_row(a, slot, lane);
+      load_row(a, slot + H, lane);
+#pragma unroll
+      for (int i = 0; i < 4 * VEC; ++i) a.v[i] += dy.v[i];
+      store_row(a, slot + H, lane);
+    }
+#pragma unroll
+    for (int i = 0; i < 4 * VEC; ++i) {
       dy.v[i] *= g.v[i];
       s1 += dy.v[i];
       s2 += dy.v[i] * xh.v[i];
@@ -440,19 +449,33 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
     for (int i = 0; i < 4 * VEC; ++i) dy.v[i] = rstd * (dy.v[i] - m1 - xh.v[i] * m2);
     store_row(dy, dz32 + (int64_t)t * H, lane);
     row_dropout(dy, seed, site, t, lane, thresh, scale);
+    if (first) {
+      store_row(dy, slot + 2 * H, lane);
+    } else {
+      Row a;
+      load_row(a, slot + 2 * H, lane);
 #pragma unroll
-    for (int i = 0; i < 4 * VEC; ++i) accp.v[i] += dy.v[i];
-    store_row_f16(dy, dpre + (int64_t)t * H, lane);
-    if (tn < T) {
-#pragma unroll
-      for (int i = 0; i < 4 * VEC; ++i) { dy.v[i] = dyn.v[i]; xh.v[i] = xhn.v[i]; }
-      rstd = rstdn;
+      for (int i = 0; i < 4 * VEC; ++i) a.v[i] += dy.v[i];
+      store_row(a, slot + 2 * H, lane);
     }
-    t = tn;
+    store_row_f16(dy, dpre + (int64_t)t * H, lane);
+    first = false;
   }
-  block_reduce_flush<8>(accg, red, dgamma, oscale, warp, lane);
-  block_reduce_flush<8>(accb, red, dbeta, oscale, warp, lane);
-  if (dbias) block_reduce_flush<8>(accp, red, dbias, oscale, warp, lane);
+  if (first) {                    // a warp without rows still owns a slot the block reduction reads
+    Row z;
+    row_zero(z);
+    store_row(z, slot, lane);
+    store_row(z, slot + H, lane);
+    store_row(z, slot + 2 * H, lane);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 3 * H; c += LNB_WARPS * 32) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < LNB_WARPS; ++w) sum += lnb_slots[w * 3 * H + c];
+    float* out = c < H ? dgamma + c : (c < 2 * H ? dbeta + (c - H) : (dbias ? dbias + (c - 2 * H) : nullptr));
+    if (out != nullptr) atomicAdd(out, sum * oscale);
+  }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -694,8 +717,17 @@ int ln_bwd(const float* dy32, const float* y32, const float* gamma, const float*
            float* dbias, cudaStream_t st) {
   uint32_t th; float sc;
   drop_params(p, th, sc);
-  MAGB_CHECK_CUDA(launch_pdl(ln_bwd_kernel, dim3(grid_rows_8w(T)), dim3(256), 0, st, dy32, y32, gamma, beta, rstd, th, sc, seed, site, T, oscale, dz32, dpre,
-                                              dgamma, dbeta, dbias));
+  constexpr size_t kSlots = (size_t)LNB_WARPS * 3 * H * sizeof(float);     // 147 456 B
+  static bool configured[kMaxDevices] = {false};
+  const int dev = current_device_slot();
+  if (!configured[dev]) {
+    MAGB_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSlots));
+    configured[dev] = true;
+  }
+  int grid = (T + LNB_WARPS - 1) / LNB_WARPS;
+  if (grid > 148) grid = 148;
+  MAGB_CHECK_CUDA(launch_pdl(ln_bwd_kernel, dim3(grid), dim3(LNB_WARPS * 32), kSlots, st, dy32, y32, gamma, beta, rstd, th, sc, seed, site, T,
+                             oscale, dz32, dpre, dgamma, dbeta, dbias));
   MAGB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

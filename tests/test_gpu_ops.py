@@ -123,6 +123,31 @@ def test_dropout_mask_is_a_pure_function_with_the_right_rate():
     assert keep_mask((10, H), 0.0, 1, 1).min().item() == 1.0
 
 
+def test_dropout_masks_are_uniform_and_independent():
+    """The mask generator (common.cuh: keyed integer hash per element, Philox under -DMAGB200_PHILOX) must behave like
+    independent Bernoulli draws: the right rate for several p, no correlation between neighbouring elements, between
+    rows, between sites and between seeds, and every column / row of a large mask close to the nominal rate."""
+    n_rows = 4096
+    for p in (0.1, 0.5):
+        keep = 1.0 - p
+        m = keep_mask((n_rows, H), p, 987654321, 18)
+        n = m.numel()
+        tol = 5.0 * math.sqrt(keep * p / n)                       # 5 sigma of the mean of n Bernoulli draws
+        assert abs(m.mean().item() - keep) < tol
+        flat = m.flatten()
+        for lag in (1, 2, 3, 4, 7, 8, 32, H, H + 1, 50 * H):      # neighbours, float4 partners, next row, next sequence
+            both = (flat[:-lag] * flat[lag:]).mean().item()
+            assert abs(both - keep * keep) < 6.0 * math.sqrt(keep * keep * (1 - keep * keep) / (n - lag)), (p, lag, both)
+        other_site = keep_mask((n_rows, H), p, 987654321, 19)
+        other_seed = keep_mask((n_rows, H), p, 987654322, 18)
+        for o in (other_site, other_seed):
+            both = (m * o).mean().item()
+            assert abs(both - keep * keep) < 6.0 * math.sqrt(keep * keep * (1 - keep * keep) / n), (p, both)
+        # per-column and per-row rates: no stuck bit positions
+        assert (m.mean(0) - keep).abs().max().item() < 6.0 * math.sqrt(keep * p / n_rows)
+        assert (m.mean(1) - keep).abs().max().item() < 6.0 * math.sqrt(keep * p / H)
+
+
 @pytest.mark.parametrize("p", [0.0, 0.1])
 def test_embed_ln_fwd_bwd(p):
     g = _g(2)
