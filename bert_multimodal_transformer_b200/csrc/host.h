@@ -138,6 +138,16 @@ int adamw_step(float* p, float* g, float* m, float* v, __half* p16, const uint8_
                cudaStream_t st);
 
 
+// ---------------------------------------------------------------- peer_optim.cu
+// data-parallel step over NVLink peer memory: flag barrier between the ranks, and reduce-scatter + AdamW + all-gather as one
+// kernel (grad_ptrs / param_ptrs: the flat fp32 buffers of every rank, this rank included; m, v, p16: local, indexed like
+// the flat buffer; only elements [slice_begin, slice_end) are touched)
+int peer_barrier(unsigned int* const* flag_ptrs, int world, int rank, unsigned int* epoch_counter, cudaStream_t st);
+int adamw_peer_step(const float* const* grad_ptrs, float* const* param_ptrs, int world, int rank, float* m, float* v,
+                    __half* p16, const uint8_t* decay_chunk, int64_t slice_begin, int64_t slice_end, float lr, float b1,
+                    float b2, float eps, float wd, int step, float gscale, const float* hyper_dev, int max_blocks,
+                    cudaStream_t st);
+
 // ---------------------------------------------------------------- xlnet_ops.cu
 struct RelAttnArgs {
   const __half* qkv = nullptr;      // [B*S][3*heads*64]  (q | k | v head projections, no bias)

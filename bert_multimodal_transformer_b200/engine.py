@@ -77,6 +77,7 @@ class BertEngine:
         self.offsets = None
         self.operands_dirty = True
         self.grad_buffers = _GradBuffers()
+        self.allocator = None          # (numel, dtype) -> tensor; the data-parallel trainer installs a peer-memory one
         self._eval_ws: Dict[tuple, torch.Tensor] = {}
         self._expected_ptrs = None
 
@@ -95,7 +96,11 @@ class BertEngine:
         if self.layout is None:
             self.layout = FlatLayout([(n, tuple(named_params[n].shape)) for n in self.order])
             self.offsets = bert_offsets_table(self.layout, self.layers, self.hidden, self.ka)
-        flat = torch.zeros(self.layout.total, dtype=torch.float32, device=dev)
+        if self.allocator is not None:
+            flat = self.allocator(self.layout.total, torch.float32)
+            flat.zero_()
+        else:
+            flat = torch.zeros(self.layout.total, dtype=torch.float32, device=dev)
         with torch.no_grad():
             for n in self.order:
                 p = named_params[n]

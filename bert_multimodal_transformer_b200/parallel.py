@@ -72,3 +72,50 @@ def sparse_rows_allreduce_(table_grad: torch.Tensor, ids: torch.Tensor, group=No
     for r in range(world):
         table_grad.index_add_(0, all_ids[r], all_rows[r])
     return table_grad
+
+
+class PeerMemory:
+    """Symmetric (peer-mapped) device buffers of the ranks of ONE node, for the NVLink-native optimizer step
+    (csrc/peer_optim.cu): torch's symmetric-memory allocator + rendezvous give every rank the addresses of every other
+    rank's copy of a buffer; the kernels of this package then read / write them directly over NVLink (no collective
+    library on that path).  PyTorch is plumbing here: allocation and the one-time exchange of the IPC handles."""
+
+    def __init__(self, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.symm = symm
+        self.device = torch.device(device)
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = world_info(group)
+        if self.world > 8:
+            raise ValueError("peer-memory optimizer: one NVLink domain of at most 8 ranks")
+        self._keep = []
+        flags = self.empty(64, torch.int32)
+        flags.zero_()
+        self.flag_ptrs = self.pointers(flags)
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=self.device)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)          # every rank has zeroed its flags before anyone signals
+
+    def empty(self, numel, dtype):
+        t = self.symm.empty(numel, dtype=dtype, device=self.device)
+        h = self.symm.rendezvous(t, self.group)
+        self._keep.append((t, h))
+        return t
+
+    def pointers(self, tensor):
+        """ctypes array of the device pointers of `tensor` (allocated by self.empty) on every rank, in rank order."""
+        import ctypes
+        for t, h in self._keep:
+            if t.data_ptr() == tensor.data_ptr():
+                ptrs = [int(p) for p in h.buffer_ptrs]
+                assert len(ptrs) == self.world and ptrs[self.rank] == tensor.data_ptr()
+                arr = (ctypes.c_void_p * 8)(*([ctypes.c_void_p(p) for p in ptrs] + [None] * (8 - len(ptrs))))
+                return arr
+        raise KeyError("tensor was not allocated through this PeerMemory")
+
+    def owned_slice(self, total):
+        """256-aligned [begin, end) of a flat buffer of `total` elements (a multiple of 256) that this rank updates."""
+        chunks = total // 256
+        b = (chunks * self.rank) // self.world * 256
+        e = (chunks * (self.rank + 1)) // self.world * 256
+        return b, e

@@ -56,7 +56,37 @@ class MagBertTrainer:
         dev = eng.flat.device
         self.dev = dev
         n = eng.layout.total
-        self.grads = torch.zeros(n, dtype=torch.float32, device=dev)
+        # Data parallel on one NVLink node: parameters and gradients move to symmetric (peer-mapped) memory and the
+        # optimizer step becomes reduce-scatter + AdamW + all-gather in ONE kernel over peer pointers
+        # (csrc/peer_optim.cu); MAGB200_PEER_ADAMW=0 (or an unavailable symmetric-memory allocator) keeps the NCCL
+        # all-reduce schedule.
+        self.peer = None
+        if self.world > 1 and os.environ.get("MAGB200_PEER_ADAMW", "0") == "1" and hasattr(eng, "allocator"):
+            try:
+                from .parallel import PeerMemory
+                pm = PeerMemory(dev, process_group)
+                eng.allocator = pm.empty
+                eng.flat = None
+                model._ensure_bound()                      # re-binds the parameters as views of a symmetric flat buffer
+                self.peer = pm
+            except Exception as e:                         # pragma: no cover  (depends on the node)
+                import warnings
+                warnings.warn(f"peer-memory optimizer unavailable ({type(e).__name__}: {e}); using the NCCL all-reduce schedule")
+                eng.allocator = None
+                if eng.flat is None:
+                    model._ensure_bound()
+                self.peer = None
+        if self.peer is not None:
+            self.grads = self.peer.empty(n, torch.float32)
+            self.grads.zero_()
+            self.peer_grad_ptrs = self.peer.pointers(self.grads)
+            self.peer_param_ptrs = self.peer.pointers(eng.flat)
+            self.peer_slice = self.peer.owned_slice(n)
+            self.peer_blocks = int(os.environ.get("MAGB200_PEER_ADAMW_BLOCKS", "0"))
+            torch.cuda.synchronize(dev)
+            torch.distributed.barrier(group=process_group)
+        else:
+            self.grads = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         self.decay = eng.layout.decay_chunks().to(dev)
@@ -139,6 +169,11 @@ class MagBertTrainer:
             if transfers:
                 self.host_loss[slot].copy_(self.loss, non_blocking=True)
             return
+        if self.peer is not None:
+            self._peer_step(i, st)
+            if transfers:
+                self.host_loss[slot].copy_(self.loss, non_blocking=True)
+            return
         if self.world > 1 and self.overlap and hasattr(eng, "backward_part"):
             self._backward_overlapped(i)
             if self.bucket_adamw:            # every slice was updated behind its all-reduce
@@ -158,6 +193,22 @@ class MagBertTrainer:
         eng.after_optimizer_step()
         if transfers:
             self.host_loss[slot].copy_(self.loss, non_blocking=True)
+
+    def _peer_step(self, i, st):
+        """backward -> [barrier: all gradients written] -> reduce-scatter + AdamW + all-gather over NVLink peer memory for
+        the slice this rank owns -> [barrier: all parameters landed, all gradients read] -> clear the local gradients,
+        re-derive the fp16 operand mirror.  No collective library call."""
+        eng, lib, pm = self.eng, L.load(), self.peer
+        eng.backward(self.train_dims, self.ws, i["input_ids"], i["token_type_ids"], i["attention_mask"], self.dlogits, self.grads)
+        L.check(lib.magb200_peer_barrier(pm.flag_ptrs, pm.world, pm.rank, L.ptr(pm.epoch), st))
+        b, e = self.peer_slice
+        L.check(lib.magb200_adamw_peer_step(self.peer_grad_ptrs, self.peer_param_ptrs, pm.world, pm.rank, L.ptr(self.exp_avg),
+                                            L.ptr(self.exp_avg_sq), L.ptr(eng.flat16), L.ptr(self.decay), b, e, self.lr,
+                                            self.betas[0], self.betas[1], self.eps, self.wd, 1, grad_unscale(self.world),
+                                            L.ptr(self.dev_hyper), self.peer_blocks, st))
+        L.check(lib.magb200_peer_barrier(pm.flag_ptrs, pm.world, pm.rank, L.ptr(pm.epoch), st))
+        self.grads.zero_()
+        eng.refresh_operands()
 
     def _adamw_range(self, s0, s1, stream_handle):
         """AdamW over elements [s0, s1) of the flat buffers (256-aligned slice) on the given stream."""

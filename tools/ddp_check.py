@@ -35,6 +35,10 @@ model = make()
 tr = MagBertTrainer(model, GLOBAL_B // world, 50, lr=1e-4, weight_decay=0.01, total_steps=0, use_cuda_graph=True)
 losses = [tr.train_step(*args(mine)) for _ in range(STEPS)]
 torch.cuda.synchronize()
+if getattr(tr, "peer", None) is not None:
+    # peer-memory optimizer: the Adam moments are sharded (each rank updates the slice it owns, the rest stays zero)
+    dist.all_reduce(tr.exp_avg)
+    print(f"rank {rank}: peer-memory optimizer step, owned slice {tr.peer_slice}", flush=True)
 ok = True
 if rank == 0:
     ref_model = make()
