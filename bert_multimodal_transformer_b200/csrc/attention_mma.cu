@@ -23,6 +23,9 @@ namespace {
 constexpr int D = 64;     // head dim
 constexpr int SP = 64;    // padded sequence tile
 constexpr int PITCH = 72; // halfs per smem row: 36 words -> fragment loads (row g, word t) hit 32 distinct banks
+constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+// softmax runs in the base-2 domain: scores and the additive mask are pre-multiplied by log2(e) so that every
+// exponential is one ex2.approx (MUFU) instead of expf's range reduction (ncu: these kernels are issue-bound)
 
 __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                          uint32_t b1) {
@@ -170,10 +173,15 @@ __global__ void __launch_bounds__(128) sdpa_fwd_mma_kernel(const __half* __restr
   __shared__ __align__(16) __half sK[SP * PITCH];
   __shared__ __align__(16) __half sV[SP * PITCH];
   __shared__ uint32_t sKeep[SP * SP / 32];
+  __shared__ float sMask[SP];        // additive key mask * log2(e); -inf beyond S
   const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int Hd = heads * D, ld = 3 * Hd;
   const __half* base = qkv + (int64_t)b * S * ld + h * D;
+  if (threadIdx.x < SP) {
+    const int j = threadIdx.x;
+    sMask[j] = j < S ? mask_add(mask ? mask + (int64_t)b * S : nullptr, j) * LOG2E : -INFINITY;
+  }
   load_tile_async(base, ld, S, sQ);
   load_tile_async(base + Hd, ld, S, sK);
   load_tile_async(base + 2 * Hd, ld, S, sV);
@@ -182,7 +190,6 @@ __global__ void __launch_bounds__(128) sdpa_fwd_mma_kernel(const __half* __restr
   __syncthreads();
   const int r0 = warp * 16;
   if (r0 >= S) return;
-  const int64_t* mrow = mask ? mask + (int64_t)b * S : nullptr;
 
   float sc[8][4];
 #pragma unroll
@@ -204,10 +211,9 @@ __global__ void __launch_bounds__(128) sdpa_fwd_mma_kernel(const __half* __restr
   for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const int j = nt * 8 + 2 * t + e;
-      const float m = j < S ? mask_add(mrow, j) : -INFINITY;
-      sc[nt][e] = sc[nt][e] * 0.125f + m;
-      sc[nt][2 + e] = sc[nt][2 + e] * 0.125f + m;
+      const float m = sMask[nt * 8 + 2 * t + e];
+      sc[nt][e] = fmaf(sc[nt][e], 0.125f * LOG2E, m);
+      sc[nt][2 + e] = fmaf(sc[nt][2 + e], 0.125f * LOG2E, m);
       mx0 = fmaxf(mx0, sc[nt][e]);
       mx1 = fmaxf(mx1, sc[nt][2 + e]);
     }
@@ -221,8 +227,8 @@ __global__ void __launch_bounds__(128) sdpa_fwd_mma_kernel(const __half* __restr
   for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      sc[nt][e] = expf(sc[nt][e] - mx0);          // exp(-inf) = 0 for padded keys
-      sc[nt][2 + e] = expf(sc[nt][2 + e] - mx1);
+      sc[nt][e] = ex2_approx(sc[nt][e] - mx0);          // 2^(-inf) = 0 for padded keys
+      sc[nt][2 + e] = ex2_approx(sc[nt][2 + e] - mx1);
       sum0 += sc[nt][e];
       sum1 += sc[nt][2 + e];
     }
@@ -234,8 +240,8 @@ __global__ void __launch_bounds__(128) sdpa_fwd_mma_kernel(const __half* __restr
   const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
   const int i0 = r0 + g, i1 = r0 + g + 8;
   if (lse != nullptr && t == 0) {
-    if (i0 < S) lse[((int64_t)b * heads + h) * S + i0] = mx0 + logf(sum0);
-    if (i1 < S) lse[((int64_t)b * heads + h) * S + i1] = mx1 + logf(sum1);
+    if (i0 < S) lse[((int64_t)b * heads + h) * S + i0] = mx0 * LN2 + logf(sum0);      // natural-log lse (the ABI's unit)
+    if (i1 < S) lse[((int64_t)b * heads + h) * S + i1] = mx1 * LN2 + logf(sum1);
   }
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
@@ -574,7 +580,7 @@ __global__ void __launch_bounds__(256) sdpa_bwd_mma8_kernel(const __half* __rest
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     if (half == 0) {
       sm.Dq[i] = acc;
-      sm.lse[i] = i < S ? lse[((int64_t)b * heads + h) * S + i] : 0.f;
+      sm.lse[i] = i < S ? lse[((int64_t)b * heads + h) * S + i] * LOG2E : 0.f;          // base-2 domain
     }
   }
   async_wait_all();
@@ -611,7 +617,7 @@ __global__ void __launch_bounds__(256) sdpa_bwd_mma8_kernel(const __half* __rest
         mma16816(dp[j], av[0], av[1], av[2], av[3], bo[0], bo[1]);
       }
     }
-    const float m0 = k0 < S ? mask_add(mrow, k0) : 0.f, m1 = k1 < S ? mask_add(mrow, k1) : 0.f;
+    const float m0 = k0 < S ? mask_add(mrow, k0) * LOG2E : 0.f, m1 = k1 < S ? mask_add(mrow, k1) * LOG2E : 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
 #pragma unroll
@@ -620,7 +626,7 @@ __global__ void __launch_bounds__(256) sdpa_bwd_mma8_kernel(const __half* __rest
         const int qi = (nb + j) * 8 + 2 * t + (e & 1);
         float dsv = 0.f, pdv = 0.f;
         if (key < S && qi < S) {
-          const float p = expf(st[j][e] * 0.125f + ((e < 2) ? m0 : m1) - sm.lse[qi]);
+          const float p = ex2_approx(fmaf(st[j][e], 0.125f * LOG2E, ((e < 2) ? m0 : m1) - sm.lse[qi]));
           const float ds = thresh == 0 ? 1.f : (keep_bit(sm.keep, qi * S + key) ? dscale : 0.f);
           pdv = p * ds;
           dsv = p * (dp[j][e] * ds - sm.Dq[qi]) * 0.125f;      // includes d(score)/d(qk) = 1/sqrt(64)
