@@ -144,9 +144,9 @@ int adamw_step(float* p, float* g, float* m, float* v, __half* p16, const uint8_
 // the flat buffer; only elements [slice_begin, slice_end) are touched)
 int peer_barrier(unsigned int* const* flag_ptrs, int world, int rank, unsigned int* epoch_counter, cudaStream_t st);
 int adamw_peer_step(const float* const* grad_ptrs, float* const* param_ptrs, int world, int rank, float* m, float* v,
-                    __half* p16, const uint8_t* decay_chunk, int64_t slice_begin, int64_t slice_end, float lr, float b1,
-                    float b2, float eps, float wd, int step, float gscale, const float* hyper_dev, int max_blocks,
-                    cudaStream_t st);
+                    __half* p16, const uint8_t* decay_chunk, int64_t slice_begin, int64_t slice_end, int64_t clean_begin,
+                    int64_t clean_end, float lr, float b1, float b2, float eps, float wd, int step, float gscale,
+                    const float* hyper_dev, int max_blocks, cudaStream_t st);
 
 // ---------------------------------------------------------------- xlnet_ops.cu
 struct RelAttnArgs {

@@ -83,6 +83,7 @@ class MagBertTrainer:
             self.peer_param_ptrs = self.peer.pointers(eng.flat)
             self.peer_slice = self.peer.owned_slice(n)
             self.peer_blocks = int(os.environ.get("MAGB200_PEER_ADAMW_BLOCKS", "0"))
+            self.peer_overlap = os.environ.get("MAGB200_PEER_OVERLAP", "1") == "1"
             torch.cuda.synchronize(dev)
             torch.distributed.barrier(group=process_group)
         else:
@@ -134,7 +135,7 @@ class MagBertTrainer:
         self._train_graph_resident = None
         self._eval_graph_resident = None
         self.stream = torch.cuda.Stream(device=dev)
-        self.comm_stream = torch.cuda.Stream(device=dev)
+        self.comm_stream = torch.cuda.Stream(device=dev, priority=-1)   # its kernels go first whenever an SM has room
         self.overlap = overlap_allreduce
         self.sparse_embedding_allreduce = os.environ.get("MAGB200_SPARSE_EMB_ALLREDUCE", "1") == "1" and \
             hasattr(eng, "vocab") and hasattr(eng, "backward_part")
@@ -170,7 +171,10 @@ class MagBertTrainer:
                 self.host_loss[slot].copy_(self.loss, non_blocking=True)
             return
         if self.peer is not None:
-            self._peer_step(i, st)
+            if self.overlap and self.peer_overlap and hasattr(eng, "backward_part"):
+                self._peer_step_overlapped(i)
+            else:
+                self._peer_step(i, st)
             if transfers:
                 self.host_loss[slot].copy_(self.loss, non_blocking=True)
             return
@@ -194,21 +198,83 @@ class MagBertTrainer:
         if transfers:
             self.host_loss[slot].copy_(self.loss, non_blocking=True)
 
+    def _peer_adamw(self, owned, clean, stream_handle):
+        """csrc/peer_optim.cu on one bucket: reduce + AdamW + broadcast of `owned`, clean-up (clear gradients, recast the
+        fp16 mirror) of `clean`; both (begin, end) in elements of the flat buffers, 256-aligned, possibly empty."""
+        eng, lib, pm = self.eng, L.load(), self.peer
+        L.check(lib.magb200_adamw_peer_step(self.peer_grad_ptrs, self.peer_param_ptrs, pm.world, pm.rank, L.ptr(self.exp_avg),
+                                            L.ptr(self.exp_avg_sq), L.ptr(eng.flat16), L.ptr(self.decay), owned[0], owned[1],
+                                            clean[0], clean[1], self.lr, self.betas[0], self.betas[1], self.eps, self.wd, 1,
+                                            grad_unscale(self.world), L.ptr(self.dev_hyper), self.peer_blocks, stream_handle))
+
+    def _peer_barrier(self, stream_handle):
+        pm = self.peer
+        L.check(L.load().magb200_peer_barrier(pm.flag_ptrs, pm.world, pm.rank, L.ptr(pm.epoch), stream_handle))
+
     def _peer_step(self, i, st):
         """backward -> [barrier: all gradients written] -> reduce-scatter + AdamW + all-gather over NVLink peer memory for
         the slice this rank owns -> [barrier: all parameters landed, all gradients read] -> clear the local gradients,
         re-derive the fp16 operand mirror.  No collective library call."""
-        eng, lib, pm = self.eng, L.load(), self.peer
+        eng = self.eng
         eng.backward(self.train_dims, self.ws, i["input_ids"], i["token_type_ids"], i["attention_mask"], self.dlogits, self.grads)
-        L.check(lib.magb200_peer_barrier(pm.flag_ptrs, pm.world, pm.rank, L.ptr(pm.epoch), st))
-        b, e = self.peer_slice
-        L.check(lib.magb200_adamw_peer_step(self.peer_grad_ptrs, self.peer_param_ptrs, pm.world, pm.rank, L.ptr(self.exp_avg),
-                                            L.ptr(self.exp_avg_sq), L.ptr(eng.flat16), L.ptr(self.decay), b, e, self.lr,
-                                            self.betas[0], self.betas[1], self.eps, self.wd, 1, grad_unscale(self.world),
-                                            L.ptr(self.dev_hyper), self.peer_blocks, st))
-        L.check(lib.magb200_peer_barrier(pm.flag_ptrs, pm.world, pm.rank, L.ptr(pm.epoch), st))
-        self.grads.zero_()
-        eng.refresh_operands()
+        self._peer_barrier(st)
+        self._peer_adamw(self.peer_slice, (0, 0), st)
+        self._peer_barrier(st)
+        self._peer_adamw((0, 0), (0, eng.layout.total), st)
+        eng.after_optimizer_step()
+
+    def _peer_step_overlapped(self, i):
+        """The peer-memory optimizer step bucket by bucket behind the backward pass (same pieces as _backward_overlapped).
+
+        communication stream, per bucket (a layer group; at the end embeddings and pooler / MAG / classifier):
+            wait for the local backward of the bucket -> barrier (every rank has written the bucket's gradients, and has
+            finished the previous bucket's kernel) -> one kernel: reduce + AdamW + broadcast of the 1/world of the bucket
+            this rank owns, plus the clean-up of the PREVIOUS bucket (clear its gradients, recast the parameters the
+            peers stored into it to fp16)
+        then a last barrier and the clean-up of the last buckets.  The main stream only runs backward; what remains after
+        it is the bottom bucket.  Ownership is per bucket (every rank owns a piece of every bucket), so all ranks work
+        on every bucket and the NVLink traffic of a bucket is spread over all links."""
+        eng = self.eng
+        main = torch.cuda.current_stream(self.dev)
+        side = self.comm_stream
+        side_h = ctypes.c_void_p(side.cuda_stream)
+        Ln = eng.layers
+        ng = max(1, min(Ln, int(os.environ.get("MAGB200_ALLREDUCE_GROUPS", "12"))))
+        cuts = sorted({(k * Ln) // ng for k in range(ng + 1)}, reverse=True)
+        groups = [(cuts[k + 1], cuts[k]) for k in range(len(cuts) - 1)]
+        args = (self.train_dims, self.ws, i["input_ids"], i["token_type_ids"], i["attention_mask"], self.dlogits,
+                self.grads)
+        total = eng.layout.total
+        tail0 = int(eng.offsets[L.OFF_POOL_W])
+        W, r = self.peer.world, self.peer.rank
+
+        def piece(s, e):
+            chunk = -(-(e - s) // (W * 256)) * 256
+            b = min(e, s + r * chunk)
+            return b, min(e, b + chunk)
+
+        prev = (0, 0)
+        for gi, (lo, hi) in enumerate(groups):
+            last = gi == len(groups) - 1
+            eng.backward_part(*args, hi - 1, lo, (1 if gi == 0 else 0) | (2 if last else 0))
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            s, e = eng.layer_grad_range(lo, hi)
+            with torch.cuda.stream(side):
+                self._peer_barrier(side_h)
+                self._peer_adamw(piece(s, e), prev, side_h)
+            prev = (s, e)
+        lo0 = eng.layer_grad_range(groups[-1][0], groups[-1][1])[0]
+        with torch.cuda.stream(side):
+            self._peer_barrier(side_h)
+            self._peer_adamw(piece(0, lo0), prev, side_h)
+            self._peer_adamw(piece(tail0, total), (0, 0), side_h)
+            self._peer_barrier(side_h)
+            self._peer_adamw((0, 0), (0, lo0), side_h)
+            self._peer_adamw((0, 0), (tail0, total), side_h)
+        main.wait_stream(side)
+        eng.after_optimizer_step()
 
     def _adamw_range(self, s0, s1, stream_handle):
         """AdamW over elements [s0, s1) of the flat buffers (256-aligned slice) on the given stream."""

@@ -222,25 +222,28 @@ typedef struct magb200_bert_dims {
   float p_hidden, p_attn, p_mag, p_cls;               /* dropout probabilities (0 = eval) */
   float grad_scale;                                    /* loss scale carried by every gradient in backward */
   uint64_t seed;                                       /* dropout seed of this step */
-  const uint64_t* seed_dev;                            /* Data-parallel optimizer step over NVLink peer memory (one node, world <= 8; multimodal_driver.py:378-386 under
- * data parallelism): every rank's flat fp32 parameters and gradients live in symmetric memory, grad_ptrs[q] / param_ptrs[q]
+  const uint64_t* seed_dev;                            /* if non-NULL the kernels read the seed from this device word
+                                                          at run time (lets a captured CUDA graph change seed per replay) */
+} magb200_bert_dims;
+
+/* Data-parallel optimizer step over NVLink peer memory (one node, world <= 8; multimodal_driver.py:378-386 under data
+ * parallelism): every rank's flat fp32 parameters and gradients live in symmetric memory, grad_ptrs[q] / param_ptrs[q]
  * are rank q's buffers as mapped in THIS process (host arrays of device pointers, this rank included).
  * magb200_adamw_peer_step: for the 256-aligned slice [slice_begin, slice_end) this rank owns -- sums the gradients of all
  * ranks in rank order (P2P loads), applies the transformers-3.0.2 AdamW of magb200_adamw_step to its local moments, and
  * stores the updated parameters into every rank's buffer (P2P stores) plus the local fp16 mirror: reduce-scatter + AdamW +
- * all-gather in one kernel; max_blocks > 0 bounds the grid (SMs left to concurrent GEMMs).
+ * all-gather in one kernel; max_blocks > 0 bounds the grid (SMs left to concurrent GEMMs).  [clean_begin, clean_end) is a
+ * range all ranks finished earlier (a barrier lies between): its local gradients are cleared and the parameters the peers
+ * stored into it are recast into the local fp16 mirror (empty range: nothing).
  * magb200_peer_barrier: flag barrier between the ranks (flag_ptrs[q]: rank q's flag array of >= world uint32 in symmetric
  * memory, zero-initialised; epoch_counter: one local device uint32, zero-initialised, advanced by the kernel itself so a
  * captured graph can be replayed). */
 int magb200_peer_barrier(void* const* flag_ptrs, int world, int rank, void* epoch_counter, void* stream);
 int magb200_adamw_peer_step(const void* const* grad_ptrs, void* const* param_ptrs, int world, int rank, float* exp_avg,
                             float* exp_avg_sq, void* p16, const uint8_t* decay_chunk, int64_t slice_begin, int64_t slice_end,
-                            float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_unscale,
-                            const float* hyper_dev, int max_blocks, void* stream);
-
-/* if non-NULL the kernels read the seed from this device word
-                                                          at run time (lets a captured CUDA graph change seed per replay) */
-} magb200_bert_dims;
+                            int64_t clean_begin, int64_t clean_end, float lr, float beta1, float beta2, float eps,
+                            float weight_decay, int step, float grad_unscale, const float* hyper_dev, int max_blocks,
+                            void* stream);
 
 size_t magb200_bert_workspace_bytes(const magb200_bert_dims* dims);
 /* params -> params16 (cast) + packed MAG gate matrix; call after the master weights change */

@@ -29,6 +29,17 @@ def test_library_exports_every_declared_symbol(lib):
     assert lib.magb200_version() == 100
 
 
+def test_header_is_plain_c():
+    """include/magb200.h is the C-ABI contract: it must parse as C (no C++ constructs, every declaration at file scope)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for h in sorted(os.listdir(os.path.join(root, "include"))):
+        if h.endswith(".h"):
+            r = subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-x", "c", os.path.join(root, "include", h)],
+                               capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
+
+
 def test_dims_struct_matches_header():
     from bert_multimodal_transformer_b200 import _lib
     hdr = open(os.path.join(ROOT, "include", "magb200.h")).read()
