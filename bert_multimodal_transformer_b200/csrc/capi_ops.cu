@@ -209,11 +209,24 @@ int magb200_peer_barrier(void* const* flag_ptrs, int world, int rank, void* epoc
 
 int magb200_adamw_peer_step(const void* const* grad_ptrs, void* const* param_ptrs, int world, int rank, float* exp_avg,
                             float* exp_avg_sq, void* p16, const uint8_t* decay_chunk, int64_t slice_begin, int64_t slice_end,
-                            int64_t clean_begin, int64_t clean_end, float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_unscale,
-                            const float* hyper_dev, int max_blocks, void* stream) {
+                            int64_t clean_begin, int64_t clean_end, float lr, float beta1, float beta2, float eps,
+                            float weight_decay, int step, float grad_unscale, const float* hyper_dev, int max_blocks,
+                            const uint8_t* row_any, int row_mode, int64_t table_begin, int table_rows, int row_len,
+                            void* stream) {
   return adamw_peer_step(reinterpret_cast<const float* const*>(grad_ptrs), reinterpret_cast<float* const*>(param_ptrs), world,
                          rank, exp_avg, exp_avg_sq, reinterpret_cast<__half*>(p16), decay_chunk, slice_begin, slice_end, clean_begin,
-                         clean_end, lr, beta1, beta2, eps, weight_decay, step, grad_unscale, hyper_dev, max_blocks, ST);
+                         clean_end, lr, beta1, beta2, eps, weight_decay, step, grad_unscale, hyper_dev, max_blocks, row_any, row_mode,
+                         table_begin, table_rows, row_len, ST);
+}
+
+int magb200_peer_mark_rows(const int64_t* ids, int n, int vocab, void* marks, void* counter, void* stream) {
+  return peer_mark_rows(ids, n, vocab, reinterpret_cast<unsigned int*>(marks), reinterpret_cast<unsigned int*>(counter), ST);
+}
+
+int magb200_peer_combine_marks(const void* const* mark_ptrs, int world, const void* counter, int vocab, uint8_t* row_any,
+                               void* stream) {
+  return peer_combine_marks(reinterpret_cast<const unsigned int* const*>(mark_ptrs), world,
+                            reinterpret_cast<const unsigned int*>(counter), vocab, row_any, ST);
 }
 
 size_t magb200_bert_workspace_bytes(const magb200_bert_dims* dims) { return bert_workspace_bytes(*dims); }

@@ -17,6 +17,9 @@
 // once and copied), and no collective library kernel competes with the backward GEMMs for SMs.
 // Ordering between ranks is a flag barrier in symmetric memory (peer_barrier_kernel): "all gradients written" before,
 // "all parameters written / all gradients read" after.
+// The trainer issues it bucket by bucket behind the backward pass (every rank owns 1 / world of every bucket), and splits
+// the word-embedding matrix by the rows the step touched (RowTable below), so the work left when backward ends is the
+// bottom layer group and a few thousand embedding rows.
 #include "common.cuh"
 #include "host.h"
 
@@ -41,6 +44,27 @@ __device__ __forceinline__ void st_peer_f4(float* p, const float4& v) {
 struct AdamConsts {
   float lr, b1, b2, eps, wd, step_size, gscale;
 };
+
+// Row-sparse table inside a bucket (the word-embedding matrix: a step touches at most batch * seq of its 30522 rows).
+// any[row] != 0: some rank has a gradient for the row in this step (peer_combine_marks_kernel).  A row nobody touched has
+// gradient exactly zero, so its update (moment decay + weight decay) needs no gradient exchange and does not depend on
+// the backward pass: mode 1 ("early", issued before backward) updates and broadcasts exactly those rows; mode 2 ("late",
+// after backward) handles the touched rows and everything outside the table.  Mode 0: dense, no table.
+struct RowTable {
+  const uint8_t* any;
+  int64_t begin4, n4;      // the table in float4 units of the flat buffer
+  int row_len4;
+  int mode;
+};
+enum { ROW_SKIP = 0, ROW_ZERO_GRAD = 1, ROW_FULL = 2 };
+__device__ __forceinline__ int classify(const RowTable& t, int64_t i) {
+  if (t.mode == 0) return ROW_FULL;
+  const int64_t rel = i - t.begin4;
+  if (rel < 0 || rel >= t.n4) return t.mode == 1 ? ROW_SKIP : ROW_FULL;
+  const bool touched = t.any[rel / t.row_len4] != 0;
+  if (t.mode == 1) return touched ? ROW_SKIP : ROW_ZERO_GRAD;
+  return touched ? ROW_FULL : ROW_SKIP;
+}
 
 // one float4 of the owned slice: gradients of all ranks (already loaded, fixed rank order) -> moments, parameters -> every rank
 __device__ __forceinline__ void adamw_peer_element(const PeerPtrs& peers, int world, int rank, const float4* g, float* m,
@@ -84,7 +108,8 @@ __global__ void __launch_bounds__(256) adamw_peer_kernel(const PeerPtrs peers, i
                                                          float* __restrict__ v, __half* __restrict__ p16,
                                                          const uint8_t* __restrict__ decay_chunk, int64_t begin4,
                                                          int64_t end4, int64_t clean_begin4, int64_t clean_end4,
-                                                         AdamConsts c, int rank, const float* __restrict__ hyper) {
+                                                         AdamConsts c, int rank, const float* __restrict__ hyper,
+                                                         const RowTable table) {
   if (hyper != nullptr) {
     c.lr = hyper[0];
     c.step_size = hyper[1];
@@ -92,26 +117,30 @@ __global__ void __launch_bounds__(256) adamw_peer_kernel(const PeerPtrs peers, i
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int64_t i = begin4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   // two elements per trip: 2 * world remote loads in flight per thread (NVLink latency is microseconds)
-  for (; i + stride < end4; i += 2 * stride) {
+  for (; i < end4; i += 2 * stride) {
+    const int64_t i1 = i + stride;
+    const int k0 = classify(table, i);
+    const int k1 = i1 < end4 ? classify(table, i1) : ROW_SKIP;
     float4 g0[kMaxPeers], g1[kMaxPeers];
 #pragma unroll
     for (int q = 0; q < kMaxPeers; ++q)
       if (q < world) {
-        g0[q] = ld_peer_f4(peers.grad[q] + 4 * i);
-        g1[q] = ld_peer_f4(peers.grad[q] + 4 * (i + stride));
+        g0[q] = k0 == ROW_FULL ? ld_peer_f4(peers.grad[q] + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        g1[q] = k1 == ROW_FULL ? ld_peer_f4(peers.grad[q] + 4 * i1) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-    adamw_peer_element(peers, world, rank, g0, m, v, p16, decay_chunk, i, c);
-    adamw_peer_element(peers, world, rank, g1, m, v, p16, decay_chunk, i + stride, c);
-  }
-  if (i < end4) {
-    float4 g0[kMaxPeers];
-#pragma unroll
-    for (int q = 0; q < kMaxPeers; ++q)
-      if (q < world) g0[q] = ld_peer_f4(peers.grad[q] + 4 * i);
-    adamw_peer_element(peers, world, rank, g0, m, v, p16, decay_chunk, i, c);
+    if (k0 != ROW_SKIP) adamw_peer_element(peers, world, rank, g0, m, v, p16, decay_chunk, i, c);
+    if (k1 != ROW_SKIP) adamw_peer_element(peers, world, rank, g1, m, v, p16, decay_chunk, i1, c);
   }
   float* my_grad = const_cast<float*>(peers.grad[rank]);
   for (int64_t j = clean_begin4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < clean_end4; j += stride) {
+    if (table.mode != 0) {
+      // inside the table only touched rows hold gradients, and nothing reads the table's fp16 mirror
+      const int64_t rel = j - table.begin4;
+      if (rel >= 0 && rel < table.n4) {
+        if (table.any[rel / table.row_len4] != 0) reinterpret_cast<float4*>(my_grad)[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        continue;
+      }
+    }
     const float4 pp = ld_peer_f4(peers.param[rank] + 4 * j);       // written by its owner over NVLink: not through L1
     __half2 a = __floats2half2_rn(pp.x, pp.y), b = __floats2half2_rn(pp.z, pp.w);
     uint2 u;
@@ -119,6 +148,41 @@ __global__ void __launch_bounds__(256) adamw_peer_kernel(const PeerPtrs peers, i
     u.y = *reinterpret_cast<uint32_t*>(&b);
     if (p16) reinterpret_cast<uint2*>(p16)[j] = u;
     reinterpret_cast<float4*>(my_grad)[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// marks[id] = (*counter + 1) for every token id of the step's batch; the counter is advanced by the kernel itself (one
+// block, so a captured graph can be replayed).  marks live in symmetric memory: the peers read them.
+__global__ void __launch_bounds__(1024) peer_mark_rows_kernel(const int64_t* __restrict__ ids, int n, int vocab,
+                                                              unsigned int* __restrict__ marks, unsigned int* counter) {
+  __shared__ unsigned int value;
+  if (threadIdx.x == 0) value = *counter + 1;
+  __syncthreads();
+  const unsigned int val = value;
+  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+    const int64_t id = ids[t];
+    if (id >= 0 && id < vocab) marks[id] = val;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *counter = val;
+}
+struct PeerMarks {
+  const unsigned int* mark[kMaxPeers];
+};
+// any[row] = 1 if some rank marked the row in this step (call after a barrier that follows every rank's marking)
+__global__ void peer_combine_marks_kernel(const PeerMarks pm, int world, const unsigned int* __restrict__ counter, int vocab,
+                                          uint8_t* __restrict__ any) {
+  const unsigned int val = *counter;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < vocab; r += gridDim.x * blockDim.x) {
+    bool hit = false;
+#pragma unroll
+    for (int q = 0; q < kMaxPeers; ++q)
+      if (q < world) {
+        unsigned int x;
+        asm volatile("ld.global.relaxed.sys.u32 %0, [%1];" : "=r"(x) : "l"(pm.mark[q] + r) : "memory");
+        hit |= x == val;
+      }
+    any[r] = hit ? 1 : 0;
   }
 }
 
@@ -161,15 +225,39 @@ int peer_barrier(unsigned int* const* flag_ptrs, int world, int rank, unsigned i
   return 0;
 }
 
+int peer_mark_rows(const int64_t* ids, int n, int vocab, unsigned int* marks, unsigned int* counter, cudaStream_t st) {
+  MAGB_REQUIRE(n >= 0 && vocab > 0, "peer_mark_rows: bad sizes %d / %d", n, vocab);
+  peer_mark_rows_kernel<<<1, 1024, 0, st>>>(ids, n, vocab, marks, counter);
+  MAGB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int peer_combine_marks(const unsigned int* const* mark_ptrs, int world, const unsigned int* counter, int vocab, uint8_t* any,
+                       cudaStream_t st) {
+  MAGB_REQUIRE(world >= 1 && world <= kMaxPeers, "peer_combine_marks: bad world %d", world);
+  PeerMarks pm;
+  for (int q = 0; q < kMaxPeers; ++q) pm.mark[q] = q < world ? mark_ptrs[q] : nullptr;
+  peer_combine_marks_kernel<<<(vocab + 255) / 256, 256, 0, st>>>(pm, world, counter, vocab, any);
+  MAGB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 int adamw_peer_step(const float* const* grad_ptrs, float* const* param_ptrs, int world, int rank, float* m, float* v,
                     __half* p16, const uint8_t* decay_chunk, int64_t slice_begin, int64_t slice_end, int64_t clean_begin,
                     int64_t clean_end, float lr, float b1, float b2, float eps, float wd, int step, float gscale,
-                    const float* hyper_dev, int max_blocks, cudaStream_t st) {
+                    const float* hyper_dev, int max_blocks, const uint8_t* row_any, int row_mode, int64_t table_begin,
+                    int table_rows, int row_len, cudaStream_t st) {
   MAGB_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "adamw_peer: bad world/rank %d/%d", world, rank);
   MAGB_REQUIRE(slice_begin % 256 == 0 && slice_end % 256 == 0 && slice_begin <= slice_end, "adamw_peer: slice [%lld, %lld) must be 256-aligned",
                (long long)slice_begin, (long long)slice_end);
   MAGB_REQUIRE(clean_begin % 256 == 0 && clean_end % 256 == 0 && clean_begin <= clean_end, "adamw_peer: clean-up range [%lld, %lld) must be 256-aligned",
                (long long)clean_begin, (long long)clean_end);
+  MAGB_REQUIRE(row_mode == 0 || (row_any != nullptr && row_mode >= 1 && row_mode <= 2 && table_begin % 4 == 0 && row_len % 4 == 0 &&
+                                 row_len > 0 && table_rows > 0),
+               "adamw_peer: bad row table (mode %d, begin %lld, rows %d, row length %d)", row_mode, (long long)table_begin,
+               table_rows, row_len);
   if (slice_end == slice_begin && clean_end == clean_begin) return 0;
   PeerPtrs pp;
   for (int q = 0; q < kMaxPeers; ++q) {
@@ -179,12 +267,15 @@ int adamw_peer_step(const float* const* grad_ptrs, float* const* param_ptrs, int
   AdamConsts c;
   c.lr = lr; c.b1 = b1; c.b2 = b2; c.eps = eps; c.wd = wd; c.gscale = gscale;
   c.step_size = lr * sqrtf(1.f - powf(b2, (float)step)) / (1.f - powf(b1, (float)step));
+  RowTable t;
+  t.any = row_any; t.mode = row_mode; t.begin4 = table_begin / 4; t.row_len4 = row_mode ? row_len / 4 : 1;
+  t.n4 = row_mode ? (int64_t)table_rows * (row_len / 4) : 0;
   const int64_t n4 = (slice_end - slice_begin) / 4, c4 = (clean_end - clean_begin) / 4;
   int blocks = (int)(((n4 > c4 ? n4 : c4) + 255) / 256);
   const int cap = max_blocks > 0 ? max_blocks : 148 * 8;
   if (blocks > cap) blocks = cap;
   adamw_peer_kernel<<<blocks, 256, 0, st>>>(pp, world, m, v, p16, decay_chunk, slice_begin / 4, slice_end / 4, clean_begin / 4,
-                                            clean_end / 4, c, rank, hyper_dev);
+                                            clean_end / 4, c, rank, hyper_dev, t);
   MAGB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

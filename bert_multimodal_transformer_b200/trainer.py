@@ -84,6 +84,14 @@ class MagBertTrainer:
             self.peer_slice = self.peer.owned_slice(n)
             self.peer_blocks = int(os.environ.get("MAGB200_PEER_ADAMW_BLOCKS", "0"))
             self.peer_overlap = os.environ.get("MAGB200_PEER_OVERLAP", "1") == "1"
+            # word-embedding matrix by touched rows (csrc/peer_optim.cu RowTable): marks in symmetric memory
+            self.peer_sparse_table = os.environ.get("MAGB200_PEER_SPARSE_TABLE", "1") == "1" and hasattr(eng, "vocab")
+            if self.peer_sparse_table:
+                self.peer_marks = self.peer.empty(eng.vocab, torch.int32)
+                self.peer_marks.zero_()
+                self.peer_mark_ptrs = self.peer.pointers(self.peer_marks)
+                self.peer_mark_counter = torch.zeros(1, dtype=torch.int32, device=dev)
+                self.peer_row_any = torch.zeros(eng.vocab, dtype=torch.uint8, device=dev)
             torch.cuda.synchronize(dev)
             torch.distributed.barrier(group=process_group)
         else:
@@ -198,14 +206,18 @@ class MagBertTrainer:
         if transfers:
             self.host_loss[slot].copy_(self.loss, non_blocking=True)
 
-    def _peer_adamw(self, owned, clean, stream_handle):
+    def _peer_adamw(self, owned, clean, stream_handle, row_mode=0):
         """csrc/peer_optim.cu on one bucket: reduce + AdamW + broadcast of `owned`, clean-up (clear gradients, recast the
-        fp16 mirror) of `clean`; both (begin, end) in elements of the flat buffers, 256-aligned, possibly empty."""
+        fp16 mirror) of `clean`; both (begin, end) in elements of the flat buffers, 256-aligned, possibly empty.
+        row_mode 1 / 2: the word-embedding matrix by untouched / touched rows (magb200.h)."""
         eng, lib, pm = self.eng, L.load(), self.peer
+        table = (L.ptr(self.peer_row_any), row_mode, int(eng.offsets[L.OFF_WORD]), eng.vocab, eng.hidden) if row_mode else \
+            (None, 0, 0, 0, 0)
         L.check(lib.magb200_adamw_peer_step(self.peer_grad_ptrs, self.peer_param_ptrs, pm.world, pm.rank, L.ptr(self.exp_avg),
                                             L.ptr(self.exp_avg_sq), L.ptr(eng.flat16), L.ptr(self.decay), owned[0], owned[1],
                                             clean[0], clean[1], self.lr, self.betas[0], self.betas[1], self.eps, self.wd, 1,
-                                            grad_unscale(self.world), L.ptr(self.dev_hyper), self.peer_blocks, stream_handle))
+                                            grad_unscale(self.world), L.ptr(self.dev_hyper), self.peer_blocks, *table,
+                                            stream_handle))
 
     def _peer_barrier(self, stream_handle):
         pm = self.peer
@@ -253,6 +265,22 @@ class MagBertTrainer:
             b = min(e, s + r * chunk)
             return b, min(e, b + chunk)
 
+        lo0 = eng.layer_grad_range(groups[-1][0], groups[-1][1])[0]
+        sparse = self.peer_sparse_table
+        if sparse:
+            # the table rows no rank touches in this step: their update needs no gradient, so it goes first and hides
+            # under the whole backward pass (all ranks have finished forward once the barrier is passed)
+            lib, pm = L.load(), self.peer
+            L.check(lib.magb200_peer_mark_rows(L.ptr(i["input_ids"]), self.B * self.S, eng.vocab, L.ptr(self.peer_marks),
+                                               L.ptr(self.peer_mark_counter), L.current_stream()))
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                self._peer_barrier(side_h)
+                L.check(lib.magb200_peer_combine_marks(self.peer_mark_ptrs, pm.world, L.ptr(self.peer_mark_counter), eng.vocab,
+                                                       L.ptr(self.peer_row_any), side_h))
+                self._peer_adamw(piece(0, lo0), (0, 0), side_h, row_mode=1)
         prev = (0, 0)
         for gi, (lo, hi) in enumerate(groups):
             last = gi == len(groups) - 1
@@ -265,14 +293,14 @@ class MagBertTrainer:
                 self._peer_barrier(side_h)
                 self._peer_adamw(piece(s, e), prev, side_h)
             prev = (s, e)
-        lo0 = eng.layer_grad_range(groups[-1][0], groups[-1][1])[0]
+        mode = 2 if sparse else 0
         with torch.cuda.stream(side):
             self._peer_barrier(side_h)
-            self._peer_adamw(piece(0, lo0), prev, side_h)
-            self._peer_adamw(piece(tail0, total), (0, 0), side_h)
+            self._peer_adamw(piece(tail0, total), prev, side_h)
+            self._peer_adamw(piece(0, lo0), (0, 0), side_h, row_mode=mode)
             self._peer_barrier(side_h)
-            self._peer_adamw((0, 0), (0, lo0), side_h)
             self._peer_adamw((0, 0), (tail0, total), side_h)
+            self._peer_adamw((0, 0), (0, lo0), side_h, row_mode=mode)
         main.wait_stream(side)
         eng.after_optimizer_step()
 

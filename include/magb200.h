@@ -243,7 +243,17 @@ int magb200_adamw_peer_step(const void* const* grad_ptrs, void* const* param_ptr
                             float* exp_avg_sq, void* p16, const uint8_t* decay_chunk, int64_t slice_begin, int64_t slice_end,
                             int64_t clean_begin, int64_t clean_end, float lr, float beta1, float beta2, float eps,
                             float weight_decay, int step, float grad_unscale, const float* hyper_dev, int max_blocks,
+                            const uint8_t* row_any, int row_mode, int64_t table_begin, int table_rows, int row_len,
                             void* stream);
+/* Row-sparse table inside a bucket (the word-embedding matrix, bert.py:211 / nn.Embedding backward: only the rows of the
+ * step's token ids receive a gradient).  magb200_peer_mark_rows stamps marks[id] (uint32[vocab] in symmetric memory) for
+ * the batch's ids with (*counter + 1) and advances the device counter; after a barrier magb200_peer_combine_marks writes
+ * row_any[row] = 1 where any rank stamped the row.  magb200_adamw_peer_step then takes row_mode 1 (before backward: update
+ * and broadcast the table rows NO rank touched -- their gradient is exactly zero; skip everything else) or row_mode 2
+ * (after backward: touched rows and everything outside the table); row_mode 0 = dense. */
+int magb200_peer_mark_rows(const int64_t* ids, int n, int vocab, void* marks, void* counter, void* stream);
+int magb200_peer_combine_marks(const void* const* mark_ptrs, int world, const void* counter, int vocab, uint8_t* row_any,
+                               void* stream);
 
 size_t magb200_bert_workspace_bytes(const magb200_bert_dims* dims);
 /* params -> params16 (cast) + packed MAG gate matrix; call after the master weights change */

@@ -20,7 +20,7 @@ from bert_multimodal_transformer_b200.parallel import shard_batch
 from bert_multimodal_transformer_b200.trainer import MagBertTrainer
 from oracle import inputs as gen, weights
 
-LAYERS, GLOBAL_B, STEPS = 4, 16 * world, 1
+LAYERS, GLOBAL_B, STEPS = 4, 16 * world, int(os.environ.get("DDP_STEPS", "1"))
 
 def make():
     class MC: beta_shift, dropout_prob = 1.0, 0.0
