@@ -145,6 +145,7 @@ static unsigned long long* g_trace = nullptr;
 static int g_cfg = 0;
 static int g_dbg = 0;
 static int g_policy = 1;   // roles routed to the persistent pair kernel by default: forward Linears (profiles/r01_gemm_policy.txt)
+static int g_streamk_grid = 0;
 static int g_streamk = 1;  // atomic-epilogue problems (weight gradients, accumulate-into-residual dgrads, split-K forward
                            // Linears) go to the persistent pair kernel with stream-K work ranges; MAGB200_STREAMK=0 restores
                            // the round-1 policy (one-shot pair tiles / whole-tile persistent scheduling)
@@ -213,12 +214,16 @@ static int launch2p_variant(const CUtensorMap& ta, const CUtensorMap& tb, const 
   // clusters, so every cluster of the device takes part as long as each gets a few K blocks (>= 4: a range boundary
   // costs a partial-sum epilogue).  (The first stream-K version kept the tile-count bound: the 36-tile weight-gradient
   // GEMMs ran on 36 of 74 clusters -- profiles/r02_prof_gemm_bwd.raw.csv, grid 72.)
+  // MAGB200_STREAMK_GRID: 0 = every cluster, 1 = the tile-count bound again, n > 1 = at most n clusters (two stream-K
+  // GEMMs run side by side in backward -- dgrad on the main stream, wgrad on the side stream -- and share the machine).
   long long total = (long long)g.tiles_m * g.tiles_n * g.splits;
-  if (g.stream_k) {
+  int cap = max_clusters[dev];
+  if (g.stream_k && g_streamk_grid != 1) {
     total = (long long)g.tiles_m * g.tiles_n * g.kb_total / 4;
     if (total < 1) total = 1;
+    if (g_streamk_grid > 1 && g_streamk_grid < cap) cap = g_streamk_grid;
   }
-  const int ncl = total < max_clusters[dev] ? (int)total : max_clusters[dev];
+  const int ncl = total < cap ? (int)total : cap;
   cfg.gridDim = dim3(2 * ncl, 1, 1);
   MAGB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, g));
   MAGB_CHECK_CUDA(cudaGetLastError());
@@ -357,6 +362,8 @@ int gemm_launch(const GemmProblem& p, cudaStream_t st) {
     if (pol && *pol) g_policy = atoi(pol);
     const char* sk = getenv("MAGB200_STREAMK");
     if (sk && *sk) g_streamk = atoi(sk);
+    const char* skg = getenv("MAGB200_STREAMK_GRID");
+    if (skg && *skg) g_streamk_grid = atoi(skg);
     const char* tr = getenv("MAGB200_TMA_REDUCE");
     if (tr && *tr) g_tma_reduce = atoi(tr);
   }

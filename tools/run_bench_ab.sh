@@ -10,7 +10,7 @@ IFS='|' read -ra VS <<< "${VARIANTS:-X=0}"
 i=0
 for v in "${VS[@]}"; do
   i=$((i+1))
-  env $v timeout 600 python bench.py --steps ${STEPS:-100} --warmup 10 --no-cpu-baseline > gpurun_out/bench_ab$i.log 2>&1; rc=$?; echo "bench [$v] exit=$rc"
-  if [ $rc -ne 0 ]; then tail -5 gpurun_out/bench_ab$i.log | cut -c1-300; exit 1; fi
+  env $v timeout 600 python bench.py --steps ${STEPS:-100} --warmup 10 --no-cpu-baseline ${BENCH_FLAGS:-} > gpurun_out/bench_ab$i.log 2>&1; rc=$?; echo "bench [$v] exit=$rc"
+  if [ $rc -ne 0 ]; then tail -5 gpurun_out/bench_ab$i.log | cut -c1-300; continue; fi
   summ gpurun_out/bench_ab$i.log
 done
