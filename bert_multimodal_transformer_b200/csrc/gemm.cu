@@ -145,7 +145,8 @@ static unsigned long long* g_trace = nullptr;
 static int g_cfg = 0;
 static int g_dbg = 0;
 static int g_policy = 1;   // roles routed to the persistent pair kernel by default: forward Linears (profiles/r01_gemm_policy.txt)
-static int g_streamk_grid = 0;
+static int g_streamk_grid = 1;
+static int g_streamk_min = 0;
 static int g_streamk = 1;  // atomic-epilogue problems (weight gradients, accumulate-into-residual dgrads, split-K forward
                            // Linears) go to the persistent pair kernel with stream-K work ranges; MAGB200_STREAMK=0 restores
                            // the round-1 policy (one-shot pair tiles / whole-tile persistent scheduling)
@@ -211,17 +212,24 @@ static int launch2p_variant(const CUtensorMap& ta, const CUtensorMap& tb, const 
     max_clusters[dev] = n < prop.multiProcessorCount / 2 ? n : prop.multiProcessorCount / 2;
   }
   // whole-tile scheduling: never more clusters than tiles.  Stream-K: the (tile, K block) units are cut evenly over the
-  // clusters, so every cluster of the device takes part as long as each gets a few K blocks (>= 4: a range boundary
-  // costs a partial-sum epilogue).  (The first stream-K version kept the tile-count bound: the 36-tile weight-gradient
-  // GEMMs ran on 36 of 74 clusters -- profiles/r02_prof_gemm_bwd.raw.csv, grid 72.)
-  // MAGB200_STREAMK_GRID: 0 = every cluster, 1 = the tile-count bound again, n > 1 = at most n clusters (two stream-K
-  // GEMMs run side by side in backward -- dgrad on the main stream, wgrad on the side stream -- and share the machine).
+  // clusters of the launch (a range boundary costs a partial-sum epilogue, so >= 4 K blocks per cluster).
+  // Stream-K grid.  Two stream-K GEMMs run side by side in backward (dgrad on the main stream, wgrad on the side stream)
+  // and a persistent cluster owns its SM pair, so "every cluster of the device" for each of them serialises the two
+  // (measured: 3.70 -> 4.08 ms / step).  Default (MAGB200_STREAMK_GRID=1): as many clusters as output tiles, but at least
+  // MAGB200_STREAMK_MIN (the 9-tile weight gradient of the attention output Linear would otherwise crawl on 9 clusters);
+  // 0 = every cluster, n > 1 = at most n clusters.
   long long total = (long long)g.tiles_m * g.tiles_n * g.splits;
   int cap = max_clusters[dev];
-  if (g.stream_k && g_streamk_grid != 1) {
-    total = (long long)g.tiles_m * g.tiles_n * g.kb_total / 4;
-    if (total < 1) total = 1;
-    if (g_streamk_grid > 1 && g_streamk_grid < cap) cap = g_streamk_grid;
+  if (g.stream_k) {
+    long long units = (long long)g.tiles_m * g.tiles_n * g.kb_total / 4;       // >= 4 K blocks per cluster
+    if (units < 1) units = 1;
+    if (g_streamk_grid == 1) {
+      if (total < g_streamk_min) total = g_streamk_min;
+      if (total > units) total = units;
+    } else {
+      total = units;
+      if (g_streamk_grid > 1 && g_streamk_grid < cap) cap = g_streamk_grid;
+    }
   }
   const int ncl = total < cap ? (int)total : cap;
   cfg.gridDim = dim3(2 * ncl, 1, 1);
@@ -364,6 +372,8 @@ int gemm_launch(const GemmProblem& p, cudaStream_t st) {
     if (sk && *sk) g_streamk = atoi(sk);
     const char* skg = getenv("MAGB200_STREAMK_GRID");
     if (skg && *skg) g_streamk_grid = atoi(skg);
+    const char* skm = getenv("MAGB200_STREAMK_MIN");
+    if (skm && *skm) g_streamk_min = atoi(skm);
     const char* tr = getenv("MAGB200_TMA_REDUCE");
     if (tr && *tr) g_tma_reduce = atoi(tr);
   }

@@ -515,3 +515,86 @@ def test_adamw_matches_transformers_3_0_2_semantics():
     L.check(lib().magb200_adamw_step(L.ptr(pc), L.ptr(gc), L.ptr(mc), L.ptr(vc), None, L.ptr(decay_d), n, lr, b1, b2,
                                      eps, wd, 4, 1.0, 0, L.ptr(hyper), stream()))
     assert torch.equal(pc, before)
+
+
+def _ptr_array(*tensors):
+    import ctypes
+    return (ctypes.c_void_p * 8)(*([ctypes.c_void_p(t.data_ptr()) for t in tensors] + [None] * (8 - len(tensors))))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [1, 3])
+def test_peer_optimizer_kernel_equals_allreduce_then_adamw(world):
+    """csrc/peer_optim.cu with the 'peers' being `world` buffers on ONE GPU (the kernel only sees pointers): summing the
+    gradients of all ranks in the kernel + AdamW + storing the parameters into every rank's buffer must equal
+    magb200_adamw_step on the pre-summed gradient -- dense, and with the embedding table split into the early pass over
+    untouched rows and the late pass over touched rows; the clean-up range clears gradients and recasts the mirror."""
+    g = _g(21)
+    rows, H = 40, 768                      # a 'table' of 40 rows in front, 256 * 30 further elements behind it
+    n = rows * H + 256 * 30
+    p0 = torch.randn(n, generator=g).cuda()
+    grads = [(torch.randn(n, generator=g) * 0.01).cuda() for _ in range(world)]
+    touched = torch.zeros(rows, dtype=torch.bool)
+    touched[[1, 5, 6, 17, 39]] = True
+    for gr in grads:                       # untouched rows carry no gradient on any rank
+        gr[:rows * H].view(rows, H)[~touched.cuda()] = 0
+    decay = (torch.arange(n // 256) % 3 != 0).to(torch.uint8).cuda()
+    lr, b1, b2, eps, wd = 1e-3, 0.9, 0.999, 1e-6, 0.01
+    m0, v0 = torch.rand(n, generator=g).cuda() * 0.01, torch.rand(n, generator=g).cuda() * 1e-4
+
+    # expected: all-reduce (sum in rank order), then the single-GPU kernel with grad_unscale = 1 / world
+    pe, me, ve = p0.clone(), m0.clone(), v0.clone()
+    gsum = torch.zeros(n, device="cuda")
+    for gr in grads:
+        gsum += gr
+    e16 = torch.zeros(n, device="cuda", dtype=torch.float16)
+    L.check(lib().magb200_adamw_step(L.ptr(pe), L.ptr(gsum), L.ptr(me), L.ptr(ve), L.ptr(e16), L.ptr(decay), n, lr, b1, b2, eps,
+                                     wd, 2, 1.0 / world, 1, None, stream()))
+
+    def run(sparse):
+        params = [p0.clone() for _ in range(world)]
+        gs = [gr.clone() for gr in grads]
+        m, v = m0.clone(), v0.clone()
+        p16 = torch.zeros(n, device="cuda", dtype=torch.float16)
+        # 'rank 0' owns everything (one call = one rank's work); its parameter copy is params[0]
+        gp, pp = _ptr_array(*gs), _ptr_array(*params)
+        ids = torch.tensor([1, 5, 6, 17, 39, 5, 1], dtype=torch.int64, device="cuda")
+        marks = torch.zeros(rows, dtype=torch.int32, device="cuda")
+        counter = torch.zeros(1, dtype=torch.int32, device="cuda")
+        any_rows = torch.zeros(rows, dtype=torch.uint8, device="cuda")
+
+        def step(owned, clean, mode):
+            L.check(lib().magb200_adamw_peer_step(gp, pp, world, 0, L.ptr(m), L.ptr(v), L.ptr(p16), L.ptr(decay), owned[0],
+                                                  owned[1], clean[0], clean[1], lr, b1, b2, eps, wd, 2, 1.0 / world, None, 0,
+                                                  L.ptr(any_rows) if mode else None, mode, 0, rows if mode else 0,
+                                                  H if mode else 0, stream()))
+        if sparse:
+            L.check(lib().magb200_peer_mark_rows(L.ptr(ids), ids.numel(), rows, L.ptr(marks), L.ptr(counter), stream()))
+            L.check(lib().magb200_peer_combine_marks(_ptr_array(*([marks] * world)), world, L.ptr(counter), rows,
+                                                     L.ptr(any_rows), stream()))
+            assert torch.equal(any_rows.bool().cpu(), touched) and int(counter.item()) == 1
+            step((0, n), (0, 0), 1)
+            # the early pass must not have touched anything that still waits for its gradient
+            assert torch.equal(params[0][rows * H:], p0[rows * H:])
+            assert torch.equal(params[0][:rows * H].view(rows, H)[touched.cuda()], p0[:rows * H].view(rows, H)[touched.cuda()])
+            step((0, n), (0, 0), 2)
+            step((0, 0), (0, n), 2)
+        else:
+            step((0, n), (0, 0), 0)
+            step((0, 0), (0, n), 0)
+        torch.cuda.synchronize()
+        return params, gs, m, v, p16
+
+    for sparse in (False, True):
+        params, gs, m, v, p16 = run(sparse)
+        for q in range(world):
+            assert torch.equal(params[q], params[0])                 # replicas are copies of one computation
+        assert (params[0] - pe).abs().max().item() < 2e-6, sparse
+        assert (m - me).abs().max().item() < 1e-7 and (v - ve).abs().max().item() < 1e-9
+        assert gs[0].abs().max().item() == 0.0                       # the calling rank's gradients are cleared
+        if world > 1:
+            assert gs[1].abs().max().item() > 0.0                    # ... and only its own
+        tail = slice(rows * H, n)
+        assert (p16[tail].float() - e16[tail].float()).abs().max().item() < 4e-3
+        if not sparse:                                               # (nothing reads the table's fp16 mirror)
+            assert (p16.float() - e16.float()).abs().max().item() < 4e-3
