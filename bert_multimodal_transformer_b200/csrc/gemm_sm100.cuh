@@ -386,6 +386,7 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& g, const CUte
     void* out = g.out0;
     if (x.epi == EPI_STORE_F16 || x.epi == EPI_STORE_BF16 || x.epi == EPI_DGELU_F16 || x.epi == EPI_GELU_F16) es = 2;
     if (x.epi == EPI_STORE_F32_F16) { es = pass == 0 ? 4 : 2; out = pass == 0 ? g.out0 : g.out1; }
+    const bool interleave = !x.tma_red && g.dbg == 5;      // MAGB200_GEMM_CFG=500 (A/B)
 #pragma unroll 1
     for (int c = 0; c < BN / 32; c += 2) {
       uint32_t r0[32], r1[32];
@@ -395,10 +396,24 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& g, const CUte
       if (tr && c == 0) tr[1] = clock64();
       epi_chunk<BN>(g, x, c, r0);
       epi_chunk<BN>(g, x, c + 1, r1);
+      if (interleave && x.live && c * 32 < ncols) {
+        // hand this 64-column slice to the store path now: its st.global drain while the next slice is read from TMEM and
+        // converted (profiles/r02_gemm_persistent_trace.txt: staging 1.1 k + stores 1.65 k cycles per slice, back to back,
+        // and the store phase of all 8 warps coincided -- 20 B/clk/SM against the 35 B/clk the store path sustains)
+        __syncwarp();
+        const int w = min(64, ncols - c * 32);
+        stage_out(stg + c * 32 * es, PITCH, reinterpret_cast<uint8_t*>(out) + ((size_t)m_base * g.ldo + n0 + c * 32) * es,
+                  (size_t)g.ldo * es, rows, w * es, lane, x.epi == EPI_ATOMIC_F32);
+        if (x.dual16)
+          stage_out(stg + BN * 2 + c * 64, PITCH, reinterpret_cast<uint8_t*>(g.out1) + ((size_t)m_base * g.ldo + n0 + c * 32) * 2,
+                    (size_t)g.ldo * 2, rows, w * 2, lane, false);
+      }
     }
     __syncwarp();
     if (tr) tr[2] = clock64();
-    if (x.live && x.tma_red) {
+    if (interleave) {
+      // stored slice by slice above
+    } else if (x.live && x.tma_red) {
       // every lane staged its own row of each box: publish to the async proxy, then one lane hands the boxes over
       fence_proxy_async_smem();
       __syncwarp();

@@ -55,6 +55,7 @@ struct RowTable {
   int64_t begin4, n4;      // the table in float4 units of the flat buffer
   int row_len4;
   int mode;
+  int clean_what;          // clean-up range: bit 0 = recast the fp16 mirror, bit 1 = clear the gradients
 };
 enum { ROW_SKIP = 0, ROW_ZERO_GRAD = 1, ROW_FULL = 2 };
 __device__ __forceinline__ int classify(const RowTable& t, int64_t i) {
@@ -137,17 +138,20 @@ __global__ void __launch_bounds__(256) adamw_peer_kernel(const PeerPtrs peers, i
       // inside the table only touched rows hold gradients, and nothing reads the table's fp16 mirror
       const int64_t rel = j - table.begin4;
       if (rel >= 0 && rel < table.n4) {
-        if (table.any[rel / table.row_len4] != 0) reinterpret_cast<float4*>(my_grad)[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((table.clean_what & 2) && table.any[rel / table.row_len4] != 0)
+          reinterpret_cast<float4*>(my_grad)[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         continue;
       }
     }
-    const float4 pp = ld_peer_f4(peers.param[rank] + 4 * j);       // written by its owner over NVLink: not through L1
-    __half2 a = __floats2half2_rn(pp.x, pp.y), b = __floats2half2_rn(pp.z, pp.w);
-    uint2 u;
-    u.x = *reinterpret_cast<uint32_t*>(&a);
-    u.y = *reinterpret_cast<uint32_t*>(&b);
-    if (p16) reinterpret_cast<uint2*>(p16)[j] = u;
-    reinterpret_cast<float4*>(my_grad)[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((table.clean_what & 1) && p16) {
+      const float4 pp = ld_peer_f4(peers.param[rank] + 4 * j);     // written by its owner over NVLink: not through L1
+      __half2 a = __floats2half2_rn(pp.x, pp.y), b = __floats2half2_rn(pp.z, pp.w);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&a);
+      u.y = *reinterpret_cast<uint32_t*>(&b);
+      reinterpret_cast<uint2*>(p16)[j] = u;
+    }
+    if (table.clean_what & 2) reinterpret_cast<float4*>(my_grad)[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -248,12 +252,13 @@ int adamw_peer_step(const float* const* grad_ptrs, float* const* param_ptrs, int
                     __half* p16, const uint8_t* decay_chunk, int64_t slice_begin, int64_t slice_end, int64_t clean_begin,
                     int64_t clean_end, float lr, float b1, float b2, float eps, float wd, int step, float gscale,
                     const float* hyper_dev, int max_blocks, const uint8_t* row_any, int row_mode, int64_t table_begin,
-                    int table_rows, int row_len, cudaStream_t st) {
+                    int table_rows, int row_len, int clean_what, cudaStream_t st) {
   MAGB_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "adamw_peer: bad world/rank %d/%d", world, rank);
   MAGB_REQUIRE(slice_begin % 256 == 0 && slice_end % 256 == 0 && slice_begin <= slice_end, "adamw_peer: slice [%lld, %lld) must be 256-aligned",
                (long long)slice_begin, (long long)slice_end);
   MAGB_REQUIRE(clean_begin % 256 == 0 && clean_end % 256 == 0 && clean_begin <= clean_end, "adamw_peer: clean-up range [%lld, %lld) must be 256-aligned",
                (long long)clean_begin, (long long)clean_end);
+  MAGB_REQUIRE(clean_what >= 0 && clean_what <= 3, "adamw_peer: clean_what %d (bit 0 recast, bit 1 clear)", clean_what);
   MAGB_REQUIRE(row_mode == 0 || (row_any != nullptr && row_mode >= 1 && row_mode <= 2 && table_begin % 4 == 0 && row_len % 4 == 0 &&
                                  row_len > 0 && table_rows > 0),
                "adamw_peer: bad row table (mode %d, begin %lld, rows %d, row length %d)", row_mode, (long long)table_begin,
@@ -270,6 +275,7 @@ int adamw_peer_step(const float* const* grad_ptrs, float* const* param_ptrs, int
   RowTable t;
   t.any = row_any; t.mode = row_mode; t.begin4 = table_begin / 4; t.row_len4 = row_mode ? row_len / 4 : 1;
   t.n4 = row_mode ? (int64_t)table_rows * (row_len / 4) : 0;
+  t.clean_what = clean_what;
   const int64_t n4 = (slice_end - slice_begin) / 4, c4 = (clean_end - clean_begin) / 4;
   int blocks = (int)(((n4 > c4 ? n4 : c4) + 255) / 256);
   const int cap = max_blocks > 0 ? max_blocks : 148 * 8;

@@ -83,7 +83,9 @@ class MagBertTrainer:
             self.peer_param_ptrs = self.peer.pointers(eng.flat)
             self.peer_slice = self.peer.owned_slice(n)
             self.peer_blocks = int(os.environ.get("MAGB200_PEER_ADAMW_BLOCKS", "0"))
-            self.peer_overlap = os.environ.get("MAGB200_PEER_OVERLAP", "1") == "1"
+            self.peer_overlap = os.environ.get("MAGB200_PEER_OVERLAP", "0") == "1"
+            self.peer_lazy_clear = os.environ.get("MAGB200_PEER_LAZY_CLEAR", "1") == "1"
+            self.peer_early_blocks = int(os.environ.get("MAGB200_PEER_EARLY_BLOCKS", "32"))
             # word-embedding matrix by touched rows (csrc/peer_optim.cu RowTable): marks in symmetric memory
             self.peer_sparse_table = os.environ.get("MAGB200_PEER_SPARSE_TABLE", "1") == "1" and hasattr(eng, "vocab")
             if self.peer_sparse_table:
@@ -165,6 +167,8 @@ class MagBertTrainer:
         if transfers:
             self._h2d(slot)
         i = self.dev_in
+        if self.peer is not None and self.peer_lazy_clear:
+            self._peer_clear_gradients_early()
         eng.forward(self.train_dims, self.ws, i["input_ids"], i["token_type_ids"], i["attention_mask"], i["visual"],
                     i["acoustic"], self.logits)
         L.check(lib.magb200_mse_loss(L.ptr(self.logits), L.ptr(i["labels"]), self.B * eng.num_labels, eng.grad_scale,
@@ -206,37 +210,95 @@ class MagBertTrainer:
         if transfers:
             self.host_loss[slot].copy_(self.loss, non_blocking=True)
 
-    def _peer_adamw(self, owned, clean, stream_handle, row_mode=0):
-        """csrc/peer_optim.cu on one bucket: reduce + AdamW + broadcast of `owned`, clean-up (clear gradients, recast the
-        fp16 mirror) of `clean`; both (begin, end) in elements of the flat buffers, 256-aligned, possibly empty.
-        row_mode 1 / 2: the word-embedding matrix by untouched / touched rows (magb200.h)."""
+    def _peer_adamw(self, owned, clean, stream_handle, row_mode=0, blocks=None):
+        """csrc/peer_optim.cu on one bucket: reduce + AdamW + broadcast of `owned`, clean-up (recast the fp16 mirror, and
+        clear the gradients unless they are cleared at the start of the next step) of `clean`; both (begin, end) in
+        elements of the flat buffers, 256-aligned, possibly empty.  row_mode 1 / 2: the word-embedding matrix by
+        untouched / touched rows (magb200.h)."""
         eng, lib, pm = self.eng, L.load(), self.peer
         table = (L.ptr(self.peer_row_any), row_mode, int(eng.offsets[L.OFF_WORD]), eng.vocab, eng.hidden) if row_mode else \
             (None, 0, 0, 0, 0)
         L.check(lib.magb200_adamw_peer_step(self.peer_grad_ptrs, self.peer_param_ptrs, pm.world, pm.rank, L.ptr(self.exp_avg),
                                             L.ptr(self.exp_avg_sq), L.ptr(eng.flat16), L.ptr(self.decay), owned[0], owned[1],
                                             clean[0], clean[1], self.lr, self.betas[0], self.betas[1], self.eps, self.wd, 1,
-                                            grad_unscale(self.world), L.ptr(self.dev_hyper), self.peer_blocks, *table,
-                                            stream_handle))
+                                            grad_unscale(self.world), L.ptr(self.dev_hyper),
+                                            self.peer_blocks if blocks is None else blocks, *table,
+                                            1 if self.peer_lazy_clear else 3, stream_handle))
 
     def _peer_barrier(self, stream_handle):
         pm = self.peer
         L.check(L.load().magb200_peer_barrier(pm.flag_ptrs, pm.world, pm.rank, L.ptr(pm.epoch), stream_handle))
 
+    def _peer_piece(self, s, e):
+        """The 256-aligned 1 / world of bucket [s, e) this rank owns (every rank owns a piece of every bucket)."""
+        W, r = self.peer.world, self.peer.rank
+        chunk = -(-(e - s) // (W * 256)) * 256
+        b = min(e, s + r * chunk)
+        return b, min(e, b + chunk)
+
+    def _peer_clear_gradients_early(self):
+        """MAGB200_PEER_LAZY_CLEAR: the gradients of the previous step are cleared on the communication stream while the
+        forward pass runs (it does not touch them) instead of in the clean-up after the optimizer step, where every byte is
+        exposed.  Safe: the previous step ended with a barrier after which no rank reads this rank's gradients."""
+        main, side = torch.cuda.current_stream(self.dev), self.comm_stream
+        ev = torch.cuda.Event()
+        ev.record(main)
+        side.wait_event(ev)
+        with torch.cuda.stream(side):
+            self.grads.zero_()
+            self._peer_clear_done = torch.cuda.Event()
+            self._peer_clear_done.record(side)
+
+    def _peer_wait_cleared(self):
+        """backward may write gradients only after the early clearing has finished"""
+        if self.peer_lazy_clear:
+            torch.cuda.current_stream(self.dev).wait_event(self._peer_clear_done)
+
+    def _peer_early_table_pass(self, i, lo0):
+        """Word-embedding rows no rank touches in this step: their update needs no gradient (it is exactly zero), so it is
+        issued before backward on the communication stream and hides under it.  All ranks have finished forward once the
+        barrier is passed, and neither forward nor backward reads an untouched row."""
+        eng, lib, pm = self.eng, L.load(), self.peer
+        main, side = torch.cuda.current_stream(self.dev), self.comm_stream
+        side_h = ctypes.c_void_p(side.cuda_stream)
+        L.check(lib.magb200_peer_mark_rows(L.ptr(i["input_ids"]), self.B * self.S, eng.vocab, L.ptr(self.peer_marks),
+                                           L.ptr(self.peer_mark_counter), L.current_stream()))
+        ev = torch.cuda.Event()
+        ev.record(main)
+        side.wait_event(ev)
+        with torch.cuda.stream(side):
+            self._peer_barrier(side_h)
+            L.check(lib.magb200_peer_combine_marks(self.peer_mark_ptrs, pm.world, L.ptr(self.peer_mark_counter), eng.vocab,
+                                                   L.ptr(self.peer_row_any), side_h))
+            self._peer_adamw(self._peer_piece(0, lo0), (0, 0), side_h, row_mode=1, blocks=self.peer_early_blocks)
+
     def _peer_step(self, i, st):
         """backward -> [barrier: all gradients written] -> reduce-scatter + AdamW + all-gather over NVLink peer memory for
-        the slice this rank owns -> [barrier: all parameters landed, all gradients read] -> clear the local gradients,
-        re-derive the fp16 operand mirror.  No collective library call."""
+        the pieces this rank owns -> [barrier: all parameters landed, all gradients read] -> clean-up (fp16 operand mirror;
+        gradients).  No collective library call.  The untouched rows of the word-embedding matrix go first, under backward."""
         eng = self.eng
+        total = eng.layout.total
+        lo0 = eng.layer_grad_range(0, 1)[0] if hasattr(eng, "layer_grad_range") else 0
+        sparse = self.peer_sparse_table
+        main, side = torch.cuda.current_stream(self.dev), self.comm_stream
+        if sparse:
+            self._peer_early_table_pass(i, lo0)
+        self._peer_wait_cleared()
         eng.backward(self.train_dims, self.ws, i["input_ids"], i["token_type_ids"], i["attention_mask"], self.dlogits, self.grads)
+        main.wait_stream(side)             # early table pass / early clearing of the gradients
+        mode = 2 if sparse else 0
         self._peer_barrier(st)
-        self._peer_adamw(self.peer_slice, (0, 0), st)
+        self._peer_adamw(self._peer_piece(lo0, total), (0, 0), st)
+        self._peer_adamw(self._peer_piece(0, lo0), (0, 0), st, row_mode=mode)
         self._peer_barrier(st)
-        self._peer_adamw((0, 0), (0, eng.layout.total), st)
+        self._peer_adamw((0, 0), (lo0, total), st)
+        self._peer_adamw((0, 0), (0, lo0), st, row_mode=mode)
         eng.after_optimizer_step()
 
     def _peer_step_overlapped(self, i):
-        """The peer-memory optimizer step bucket by bucket behind the backward pass (same pieces as _backward_overlapped).
+        """The peer-memory optimizer step bucket by bucket behind the backward pass (same pieces as _backward_overlapped;
+        MAGB200_PEER_OVERLAP=1).  Measured SLOWER than _peer_step at 2 GPUs (4.24 vs 4.16 ms / step): the reduce kernels
+        take SM slots, L2 and HBM bandwidth from the backward GEMMs, which are sensitive to all three.  Kept for A/B.
 
         communication stream, per bucket (a layer group; at the end embeddings and pooler / MAG / classifier):
             wait for the local backward of the bucket -> barrier (every rank has written the bucket's gradients, and has
@@ -244,8 +306,7 @@ class MagBertTrainer:
             this rank owns, plus the clean-up of the PREVIOUS bucket (clear its gradients, recast the parameters the
             peers stored into it to fp16)
         then a last barrier and the clean-up of the last buckets.  The main stream only runs backward; what remains after
-        it is the bottom bucket.  Ownership is per bucket (every rank owns a piece of every bucket), so all ranks work
-        on every bucket and the NVLink traffic of a bucket is spread over all links."""
+        it is the bottom bucket."""
         eng = self.eng
         main = torch.cuda.current_stream(self.dev)
         side = self.comm_stream
@@ -258,29 +319,12 @@ class MagBertTrainer:
                 self.grads)
         total = eng.layout.total
         tail0 = int(eng.offsets[L.OFF_POOL_W])
-        W, r = self.peer.world, self.peer.rank
-
-        def piece(s, e):
-            chunk = -(-(e - s) // (W * 256)) * 256
-            b = min(e, s + r * chunk)
-            return b, min(e, b + chunk)
-
+        piece = self._peer_piece
         lo0 = eng.layer_grad_range(groups[-1][0], groups[-1][1])[0]
         sparse = self.peer_sparse_table
         if sparse:
-            # the table rows no rank touches in this step: their update needs no gradient, so it goes first and hides
-            # under the whole backward pass (all ranks have finished forward once the barrier is passed)
-            lib, pm = L.load(), self.peer
-            L.check(lib.magb200_peer_mark_rows(L.ptr(i["input_ids"]), self.B * self.S, eng.vocab, L.ptr(self.peer_marks),
-                                               L.ptr(self.peer_mark_counter), L.current_stream()))
-            ev = torch.cuda.Event()
-            ev.record(main)
-            side.wait_event(ev)
-            with torch.cuda.stream(side):
-                self._peer_barrier(side_h)
-                L.check(lib.magb200_peer_combine_marks(self.peer_mark_ptrs, pm.world, L.ptr(self.peer_mark_counter), eng.vocab,
-                                                       L.ptr(self.peer_row_any), side_h))
-                self._peer_adamw(piece(0, lo0), (0, 0), side_h, row_mode=1)
+            self._peer_early_table_pass(i, lo0)
+        self._peer_wait_cleared()
         prev = (0, 0)
         for gi, (lo, hi) in enumerate(groups):
             last = gi == len(groups) - 1

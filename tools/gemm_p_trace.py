@@ -20,7 +20,7 @@ for name, M, N, K, amn, bmn, epi, splits in SHAPES:
         L.check(lib.magb200_gemm(L.ptr(A), L.ptr(B), M, N, K, A.shape[1], B.shape[1], L.F16, L.F16, amn, bmn, epi, L.ptr(bias),
                                  L.ptr(O), L.ptr(O1) if epi == L.EPI_GELU_F16 else None, None, N, 1.0, splits, 0, 0,
                                  L.current_stream()))
-    for cfg in (9, 209):
+    for cfg in [int(c) for c in os.environ.get("TRACE_CFGS", "9,209").split(",")]:
         lib.magb200_gemm_set_debug(None, cfg)
         for _ in range(3): launch()
         torch.cuda.synchronize()
