@@ -67,18 +67,10 @@ __device__ __forceinline__ int classify(const RowTable& t, int64_t i) {
   return touched ? ROW_FULL : ROW_SKIP;
 }
 
-// one float4 of the owned slice: gradients of all ranks (already loaded, fixed rank order) -> moments, parameters -> every rank
-__device__ __forceinline__ void adamw_peer_element(const PeerPtrs& peers, int world, int rank, const float4* g, float* m,
-                                                   float* v, __half* p16, const uint8_t* decay_chunk, int64_t i,
-                                                   const AdamConsts& c) {
-  float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-  for (int q = 0; q < kMaxPeers; ++q)
-    if (q < world) { gg.x += g[q].x; gg.y += g[q].y; gg.z += g[q].z; gg.w += g[q].w; }
-  float4 pp = reinterpret_cast<const float4*>(peers.param[rank])[i];
-  float4 mm = reinterpret_cast<float4*>(m)[i];
-  float4 vv = reinterpret_cast<float4*>(v)[i];
-  const float dec = decay_chunk[i >> 6] ? c.lr * c.wd : 0.f;
+// one float4 of the owned slice: summed gradient -> moments, parameters -> every rank
+template <int W>
+__device__ __forceinline__ void adamw_peer_element(const PeerPtrs& peers, float4 gg, float4 pp, float4 mm, float4 vv,
+                                                   float* m, float* v, __half* p16, float dec, int64_t i, const AdamConsts& c) {
   float* P = &pp.x; float* G = &gg.x; float* M = &mm.x; float* V = &vv.x;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -91,8 +83,7 @@ __device__ __forceinline__ void adamw_peer_element(const PeerPtrs& peers, int wo
   reinterpret_cast<float4*>(m)[i] = mm;
   reinterpret_cast<float4*>(v)[i] = vv;
 #pragma unroll
-  for (int q = 0; q < kMaxPeers; ++q)
-    if (q < world) st_peer_f4(peers.param[q] + 4 * i, pp);
+  for (int q = 0; q < W; ++q) st_peer_f4(peers.param[q] + 4 * i, pp);
   if (p16) {
     __half2 a = __floats2half2_rn(pp.x, pp.y), b = __floats2half2_rn(pp.z, pp.w);
     uint2 u;
@@ -104,35 +95,58 @@ __device__ __forceinline__ void adamw_peer_element(const PeerPtrs& peers, int wo
 
 // [begin4, end4): the piece of a bucket this rank owns (reduce + AdamW + broadcast).
 // [clean_begin4, clean_end4): a range every rank has finished with (a barrier lies between): the parameters the peers
-// wrote into it are recast into the local fp16 operand mirror and the local gradients are cleared for the next step.
-__global__ void __launch_bounds__(256) adamw_peer_kernel(const PeerPtrs peers, int world, float* __restrict__ m,
-                                                         float* __restrict__ v, __half* __restrict__ p16,
-                                                         const uint8_t* __restrict__ decay_chunk, int64_t begin4,
-                                                         int64_t end4, int64_t clean_begin4, int64_t clean_end4,
-                                                         AdamConsts c, int rank, const float* __restrict__ hyper,
+// wrote into it are recast into the local fp16 operand mirror and the local gradients are cleared for the next step;
+// [keep_begin4, keep_end4) inside it is this rank's own piece, whose mirror the update already wrote.
+// W = number of ranks (static: the per-rank pointers and the loaded gradients stay in registers), U = float4 elements per
+// thread and trip.  All U * W remote loads and the 3 * U local ones of a trip are issued before the first is used: NVLink
+// latency is microseconds, and the first version (2 elements, loads of p / m / v only after the gradients had arrived)
+// reached 320 GB/s per direction at 2 GPUs.
+template <int W, int U>
+__global__ void __launch_bounds__(256) adamw_peer_kernel(const PeerPtrs peers, float* __restrict__ m, float* __restrict__ v,
+                                                         __half* __restrict__ p16, const uint8_t* __restrict__ decay_chunk,
+                                                         int64_t begin4, int64_t end4, int64_t clean_begin4,
+                                                         int64_t clean_end4, int64_t keep_begin4, int64_t keep_end4,
+                                                         AdamConsts c, const float* __restrict__ my_param,
+                                                         float* __restrict__ my_grad, const float* __restrict__ hyper,
                                                          const RowTable table) {
+  // my_param / my_grad = this rank's entries of `peers` (separate arguments: indexing the by-value struct with a run-time
+  // rank would copy it to local memory)
   if (hyper != nullptr) {
     c.lr = hyper[0];
     c.step_size = hyper[1];
   }
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  int64_t i = begin4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  // two elements per trip: 2 * world remote loads in flight per thread (NVLink latency is microseconds)
-  for (; i < end4; i += 2 * stride) {
-    const int64_t i1 = i + stride;
-    const int k0 = classify(table, i);
-    const int k1 = i1 < end4 ? classify(table, i1) : ROW_SKIP;
-    float4 g0[kMaxPeers], g1[kMaxPeers];
+  for (int64_t i0 = begin4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < end4; i0 += U * stride) {
+    int kind[U];
+    float4 pp[U], mm[U], vv[U], g[U][W];
 #pragma unroll
-    for (int q = 0; q < kMaxPeers; ++q)
-      if (q < world) {
-        g0[q] = k0 == ROW_FULL ? ld_peer_f4(peers.grad[q] + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        g1[q] = k1 == ROW_FULL ? ld_peer_f4(peers.grad[q] + 4 * i1) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      kind[u] = i < end4 ? classify(table, i) : ROW_SKIP;
+      if (kind[u] != ROW_SKIP) {
+        pp[u] = reinterpret_cast<const float4*>(my_param)[i];
+        mm[u] = reinterpret_cast<const float4*>(m)[i];
+        vv[u] = reinterpret_cast<const float4*>(v)[i];
       }
-    if (k0 != ROW_SKIP) adamw_peer_element(peers, world, rank, g0, m, v, p16, decay_chunk, i, c);
-    if (k1 != ROW_SKIP) adamw_peer_element(peers, world, rank, g1, m, v, p16, decay_chunk, i1, c);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+#pragma unroll
+      for (int q = 0; q < W; ++q)
+        g[u][q] = kind[u] == ROW_FULL ? ld_peer_f4(peers.grad[q] + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (kind[u] == ROW_SKIP) continue;
+      const int64_t i = i0 + u * stride;
+      float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < W; ++q) { gg.x += g[u][q].x; gg.y += g[u][q].y; gg.z += g[u][q].z; gg.w += g[u][q].w; }   // fixed rank order
+      const float dec = decay_chunk[i >> 6] ? c.lr * c.wd : 0.f;
+      adamw_peer_element<W>(peers, gg, pp[u], mm[u], vv[u], m, v, p16, dec, i, c);
+    }
   }
-  float* my_grad = const_cast<float*>(peers.grad[rank]);
   for (int64_t j = clean_begin4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < clean_end4; j += stride) {
     if (table.mode != 0) {
       // inside the table only touched rows hold gradients, and nothing reads the table's fp16 mirror
@@ -143,8 +157,8 @@ __global__ void __launch_bounds__(256) adamw_peer_kernel(const PeerPtrs peers, i
         continue;
       }
     }
-    if ((table.clean_what & 1) && p16) {
-      const float4 pp = ld_peer_f4(peers.param[rank] + 4 * j);     // written by its owner over NVLink: not through L1
+    if ((table.clean_what & 1) && p16 && !(j >= keep_begin4 && j < keep_end4)) {
+      const float4 pp = ld_peer_f4(my_param + 4 * j);              // written by its owner over NVLink: not through L1
       __half2 a = __floats2half2_rn(pp.x, pp.y), b = __floats2half2_rn(pp.z, pp.w);
       uint2 u;
       u.x = *reinterpret_cast<uint32_t*>(&a);
@@ -252,12 +266,14 @@ int adamw_peer_step(const float* const* grad_ptrs, float* const* param_ptrs, int
                     __half* p16, const uint8_t* decay_chunk, int64_t slice_begin, int64_t slice_end, int64_t clean_begin,
                     int64_t clean_end, float lr, float b1, float b2, float eps, float wd, int step, float gscale,
                     const float* hyper_dev, int max_blocks, const uint8_t* row_any, int row_mode, int64_t table_begin,
-                    int table_rows, int row_len, int clean_what, cudaStream_t st) {
+                    int table_rows, int row_len, int clean_what, int64_t keep_begin, int64_t keep_end, cudaStream_t st) {
   MAGB_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "adamw_peer: bad world/rank %d/%d", world, rank);
   MAGB_REQUIRE(slice_begin % 256 == 0 && slice_end % 256 == 0 && slice_begin <= slice_end, "adamw_peer: slice [%lld, %lld) must be 256-aligned",
                (long long)slice_begin, (long long)slice_end);
   MAGB_REQUIRE(clean_begin % 256 == 0 && clean_end % 256 == 0 && clean_begin <= clean_end, "adamw_peer: clean-up range [%lld, %lld) must be 256-aligned",
                (long long)clean_begin, (long long)clean_end);
+  MAGB_REQUIRE(keep_begin % 4 == 0 && keep_end % 4 == 0 && keep_begin <= keep_end, "adamw_peer: bad keep range [%lld, %lld)",
+               (long long)keep_begin, (long long)keep_end);
   MAGB_REQUIRE(clean_what >= 0 && clean_what <= 3, "adamw_peer: clean_what %d (bit 0 recast, bit 1 clear)", clean_what);
   MAGB_REQUIRE(row_mode == 0 || (row_any != nullptr && row_mode >= 1 && row_mode <= 2 && table_begin % 4 == 0 && row_len % 4 == 0 &&
                                  row_len > 0 && table_rows > 0),
@@ -280,8 +296,23 @@ int adamw_peer_step(const float* const* grad_ptrs, float* const* param_ptrs, int
   int blocks = (int)(((n4 > c4 ? n4 : c4) + 255) / 256);
   const int cap = max_blocks > 0 ? max_blocks : 148 * 8;
   if (blocks > cap) blocks = cap;
-  adamw_peer_kernel<<<blocks, 256, 0, st>>>(pp, world, m, v, p16, decay_chunk, slice_begin / 4, slice_end / 4, clean_begin / 4,
-                                            clean_end / 4, c, rank, hyper_dev, t);
+  // the owner's own piece inside the clean-up range keeps the fp16 mirror its update wrote
+  const int64_t keep_b = (clean_end > clean_begin) ? keep_begin / 4 : 0, keep_e = (clean_end > clean_begin) ? keep_end / 4 : 0;
+#define MAGB_PEER_LAUNCH(W_, U_)                                                                                              \
+  adamw_peer_kernel<W_, U_><<<blocks, 256, 0, st>>>(pp, m, v, p16, decay_chunk, slice_begin / 4, slice_end / 4, clean_begin / 4, \
+                                                    clean_end / 4, keep_b, keep_e, c, pp.param[rank], const_cast<float*>(pp.grad[rank]),  \
+                                                    hyper_dev, t)
+  switch (world) {
+    case 1: MAGB_PEER_LAUNCH(1, 4); break;
+    case 2: MAGB_PEER_LAUNCH(2, 4); break;
+    case 3: MAGB_PEER_LAUNCH(3, 4); break;
+    case 4: MAGB_PEER_LAUNCH(4, 4); break;
+    case 5: MAGB_PEER_LAUNCH(5, 2); break;
+    case 6: MAGB_PEER_LAUNCH(6, 2); break;
+    case 7: MAGB_PEER_LAUNCH(7, 2); break;
+    default: MAGB_PEER_LAUNCH(8, 2); break;
+  }
+#undef MAGB_PEER_LAUNCH
   MAGB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -84,7 +84,7 @@ class MagBertTrainer:
             self.peer_slice = self.peer.owned_slice(n)
             self.peer_blocks = int(os.environ.get("MAGB200_PEER_ADAMW_BLOCKS", "0"))
             self.peer_overlap = os.environ.get("MAGB200_PEER_OVERLAP", "0") == "1"
-            self.peer_lazy_clear = os.environ.get("MAGB200_PEER_LAZY_CLEAR", "1") == "1"
+            self.peer_lazy_clear = os.environ.get("MAGB200_PEER_LAZY_CLEAR", "0") == "1"   # measured slower (4.20 vs 4.16 ms at 2 GPUs)
             self.peer_early_blocks = int(os.environ.get("MAGB200_PEER_EARLY_BLOCKS", "32"))
             # word-embedding matrix by touched rows (csrc/peer_optim.cu RowTable): marks in symmetric memory
             self.peer_sparse_table = os.environ.get("MAGB200_PEER_SPARSE_TABLE", "1") == "1" and hasattr(eng, "vocab")
@@ -210,7 +210,7 @@ class MagBertTrainer:
         if transfers:
             self.host_loss[slot].copy_(self.loss, non_blocking=True)
 
-    def _peer_adamw(self, owned, clean, stream_handle, row_mode=0, blocks=None):
+    def _peer_adamw(self, owned, clean, stream_handle, row_mode=0, blocks=None, keep=(0, 0)):
         """csrc/peer_optim.cu on one bucket: reduce + AdamW + broadcast of `owned`, clean-up (recast the fp16 mirror, and
         clear the gradients unless they are cleared at the start of the next step) of `clean`; both (begin, end) in
         elements of the flat buffers, 256-aligned, possibly empty.  row_mode 1 / 2: the word-embedding matrix by
@@ -223,7 +223,7 @@ class MagBertTrainer:
                                             clean[0], clean[1], self.lr, self.betas[0], self.betas[1], self.eps, self.wd, 1,
                                             grad_unscale(self.world), L.ptr(self.dev_hyper),
                                             self.peer_blocks if blocks is None else blocks, *table,
-                                            1 if self.peer_lazy_clear else 3, stream_handle))
+                                            1 if self.peer_lazy_clear else 3, keep[0], keep[1], stream_handle))
 
     def _peer_barrier(self, stream_handle):
         pm = self.peer
@@ -291,8 +291,8 @@ class MagBertTrainer:
         self._peer_adamw(self._peer_piece(lo0, total), (0, 0), st)
         self._peer_adamw(self._peer_piece(0, lo0), (0, 0), st, row_mode=mode)
         self._peer_barrier(st)
-        self._peer_adamw((0, 0), (lo0, total), st)
-        self._peer_adamw((0, 0), (0, lo0), st, row_mode=mode)
+        self._peer_adamw((0, 0), (lo0, total), st, keep=self._peer_piece(lo0, total))
+        self._peer_adamw((0, 0), (0, lo0), st, row_mode=mode, keep=self._peer_piece(0, lo0))
         eng.after_optimizer_step()
 
     def _peer_step_overlapped(self, i):
@@ -335,16 +335,16 @@ class MagBertTrainer:
             s, e = eng.layer_grad_range(lo, hi)
             with torch.cuda.stream(side):
                 self._peer_barrier(side_h)
-                self._peer_adamw(piece(s, e), prev, side_h)
+                self._peer_adamw(piece(s, e), prev, side_h, keep=piece(*prev) if prev[1] > prev[0] else (0, 0))
             prev = (s, e)
         mode = 2 if sparse else 0
         with torch.cuda.stream(side):
             self._peer_barrier(side_h)
-            self._peer_adamw(piece(tail0, total), prev, side_h)
+            self._peer_adamw(piece(tail0, total), prev, side_h, keep=piece(*prev) if prev[1] > prev[0] else (0, 0))
             self._peer_adamw(piece(0, lo0), (0, 0), side_h, row_mode=mode)
             self._peer_barrier(side_h)
-            self._peer_adamw((0, 0), (tail0, total), side_h)
-            self._peer_adamw((0, 0), (0, lo0), side_h, row_mode=mode)
+            self._peer_adamw((0, 0), (tail0, total), side_h, keep=piece(tail0, total))
+            self._peer_adamw((0, 0), (0, lo0), side_h, row_mode=mode, keep=piece(0, lo0))
         main.wait_stream(side)
         eng.after_optimizer_step()
 

@@ -49,7 +49,8 @@ def pieces():
     ev[4].record()
     tr._peer_barrier(st)
     ev[5].record()
-    tr._peer_adamw((0, 0), (0, total), st)
+    tr._peer_adamw((0, 0), (lo0, total), st, keep=tr._peer_piece(lo0, total))
+    tr._peer_adamw((0, 0), (0, lo0), st, keep=tr._peer_piece(0, lo0))
     ev[6].record()
     eng.after_optimizer_step()
     ev[7].record()
@@ -75,8 +76,8 @@ if rank == 0:
     for n, a, m in zip(names, acc.tolist(), mx.tolist()):
         print(f"  {n:34s} {m:8.3f} {a:8.3f}")
     k = mx[3].item()
-    print(f"  kernel: {(world - 1) * own / k / 1e3:.1f} GB/s NVLink in (and out) per GPU, "
-          f"{(own * 7 + own * 0.5) / k / 1e3:.1f} GB/s local HBM")
+    print(f"  kernel: {(world - 1) * own / k:.1f} GB/s NVLink in (and out) per GPU, "
+          f"{(own * 7 + own * 0.5) / k:.1f} GB/s local HBM")
 dist.barrier()
 torch.cuda.synchronize()
 os._exit(0)
