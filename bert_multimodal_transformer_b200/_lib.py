@@ -104,7 +104,7 @@ SIGNATURES = {
     "magb200_peer_barrier": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "magb200_adamw_peer_step": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                         c_int64, c_int64, c_float, c_float, c_float, c_float, c_float, c_int, c_float, c_void_p, c_int,
-                                        c_void_p, c_int, c_int64, c_int, c_int, c_int, c_int64, c_int64, c_void_p]),
+                                        c_void_p, c_int, c_int64, c_int, c_int, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "magb200_peer_mark_rows": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "magb200_peer_combine_marks": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "magb200_bert_workspace_bytes": (c_size_t, [POINTER(BertDims)]),

@@ -212,11 +212,13 @@ int magb200_adamw_peer_step(const void* const* grad_ptrs, void* const* param_ptr
                             int64_t clean_begin, int64_t clean_end, float lr, float beta1, float beta2, float eps,
                             float weight_decay, int step, float grad_unscale, const float* hyper_dev, int max_blocks,
                             const uint8_t* row_any, int row_mode, int64_t table_begin, int table_rows, int row_len,
-                            int clean_what, int64_t keep_begin, int64_t keep_end, void* stream) {
+                            int clean_what, int64_t keep_begin, int64_t keep_end, const void* multicast_grad,
+                            void* multicast_param, void* stream) {
   return adamw_peer_step(reinterpret_cast<const float* const*>(grad_ptrs), reinterpret_cast<float* const*>(param_ptrs), world,
                          rank, exp_avg, exp_avg_sq, reinterpret_cast<__half*>(p16), decay_chunk, slice_begin, slice_end, clean_begin,
                          clean_end, lr, beta1, beta2, eps, weight_decay, step, grad_unscale, hyper_dev, max_blocks, row_any, row_mode,
-                         table_begin, table_rows, row_len, clean_what, keep_begin, keep_end, ST);
+                         table_begin, table_rows, row_len, clean_what, keep_begin, keep_end,
+                         reinterpret_cast<const float*>(multicast_grad), reinterpret_cast<float*>(multicast_param), ST);
 }
 
 int magb200_peer_mark_rows(const int64_t* ids, int n, int vocab, void* marks, void* counter, void* stream) {

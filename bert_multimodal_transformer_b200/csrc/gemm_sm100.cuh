@@ -386,7 +386,7 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& g, const CUte
     void* out = g.out0;
     if (x.epi == EPI_STORE_F16 || x.epi == EPI_STORE_BF16 || x.epi == EPI_DGELU_F16 || x.epi == EPI_GELU_F16) es = 2;
     if (x.epi == EPI_STORE_F32_F16) { es = pass == 0 ? 4 : 2; out = pass == 0 ? g.out0 : g.out1; }
-    const bool interleave = !x.tma_red && g.dbg == 5;      // MAGB200_GEMM_CFG=500 (A/B)
+    const bool interleave = !x.tma_red && g.dbg != 4;      // MAGB200_GEMM_CFG=400: store after the whole tile is staged (A/B)
 #pragma unroll 1
     for (int c = 0; c < BN / 32; c += 2) {
       uint32_t r0[32], r1[32];

@@ -147,7 +147,8 @@ int adamw_peer_step(const float* const* grad_ptrs, float* const* param_ptrs, int
                     __half* p16, const uint8_t* decay_chunk, int64_t slice_begin, int64_t slice_end, int64_t clean_begin,
                     int64_t clean_end, float lr, float b1, float b2, float eps, float wd, int step, float gscale,
                     const float* hyper_dev, int max_blocks, const uint8_t* row_any, int row_mode, int64_t table_begin,
-                    int table_rows, int row_len, int clean_what, int64_t keep_begin, int64_t keep_end, cudaStream_t st);
+                    int table_rows, int row_len, int clean_what, int64_t keep_begin, int64_t keep_end,
+                    const float* mc_grad, float* mc_param, cudaStream_t st);
 int peer_mark_rows(const int64_t* ids, int n, int vocab, unsigned int* marks, unsigned int* counter, cudaStream_t st);
 int peer_combine_marks(const unsigned int* const* mark_ptrs, int world, const unsigned int* counter, int vocab, uint8_t* any,
                        cudaStream_t st);

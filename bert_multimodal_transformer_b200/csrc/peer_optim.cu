@@ -41,6 +41,19 @@ __device__ __forceinline__ void st_peer_f4(float* p, const float4& v) {
   asm volatile("st.global.relaxed.sys.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// NVSwitch multicast (NVLS): one address that stands for the same offset in every rank's buffer.  A reducing load returns
+// the SUM over all ranks, added inside the switch (each GPU's NVLink carries the element once instead of world - 1 times);
+// a store is replicated by the switch to every rank, this one included.
+__device__ __forceinline__ float4 multimem_ld_sum_f4(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st_f4(float* mc, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 struct AdamConsts {
   float lr, b1, b2, eps, wd, step_size, gscale;
 };
@@ -82,8 +95,12 @@ __device__ __forceinline__ void adamw_peer_element(const PeerPtrs& peers, float4
   }
   reinterpret_cast<float4*>(m)[i] = mm;
   reinterpret_cast<float4*>(v)[i] = vv;
+  if constexpr (W == 0) {
+    multimem_st_f4(peers.param[0] + 4 * i, pp);          // param[0] = the multicast address
+  } else {
 #pragma unroll
-  for (int q = 0; q < W; ++q) st_peer_f4(peers.param[q] + 4 * i, pp);
+    for (int q = 0; q < W; ++q) st_peer_f4(peers.param[q] + 4 * i, pp);
+  }
   if (p16) {
     __half2 a = __floats2half2_rn(pp.x, pp.y), b = __floats2half2_rn(pp.z, pp.w);
     uint2 u;
@@ -118,7 +135,8 @@ __global__ void __launch_bounds__(256) adamw_peer_kernel(const PeerPtrs peers, f
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i0 = begin4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < end4; i0 += U * stride) {
     int kind[U];
-    float4 pp[U], mm[U], vv[U], g[U][W];
+    constexpr int NG = W == 0 ? 1 : W;        // W == 0: multicast form, grad[0] / param[0] are the multicast addresses
+    float4 pp[U], mm[U], vv[U], g[U][NG];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t i = i0 + u * stride;
@@ -132,9 +150,13 @@ __global__ void __launch_bounds__(256) adamw_peer_kernel(const PeerPtrs peers, f
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t i = i0 + u * stride;
+      if constexpr (W == 0) {
+        g[u][0] = kind[u] == ROW_FULL ? multimem_ld_sum_f4(peers.grad[0] + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
 #pragma unroll
-      for (int q = 0; q < W; ++q)
-        g[u][q] = kind[u] == ROW_FULL ? ld_peer_f4(peers.grad[q] + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < W; ++q)
+          g[u][q] = kind[u] == ROW_FULL ? ld_peer_f4(peers.grad[q] + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -142,7 +164,7 @@ __global__ void __launch_bounds__(256) adamw_peer_kernel(const PeerPtrs peers, f
       const int64_t i = i0 + u * stride;
       float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int q = 0; q < W; ++q) { gg.x += g[u][q].x; gg.y += g[u][q].y; gg.z += g[u][q].z; gg.w += g[u][q].w; }   // fixed rank order
+      for (int q = 0; q < NG; ++q) { gg.x += g[u][q].x; gg.y += g[u][q].y; gg.z += g[u][q].z; gg.w += g[u][q].w; }  // fixed rank order
       const float dec = decay_chunk[i >> 6] ? c.lr * c.wd : 0.f;
       adamw_peer_element<W>(peers, gg, pp[u], mm[u], vv[u], m, v, p16, dec, i, c);
     }
@@ -266,7 +288,8 @@ int adamw_peer_step(const float* const* grad_ptrs, float* const* param_ptrs, int
                     __half* p16, const uint8_t* decay_chunk, int64_t slice_begin, int64_t slice_end, int64_t clean_begin,
                     int64_t clean_end, float lr, float b1, float b2, float eps, float wd, int step, float gscale,
                     const float* hyper_dev, int max_blocks, const uint8_t* row_any, int row_mode, int64_t table_begin,
-                    int table_rows, int row_len, int clean_what, int64_t keep_begin, int64_t keep_end, cudaStream_t st) {
+                    int table_rows, int row_len, int clean_what, int64_t keep_begin, int64_t keep_end, const float* mc_grad,
+                    float* mc_param, cudaStream_t st) {
   MAGB_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "adamw_peer: bad world/rank %d/%d", world, rank);
   MAGB_REQUIRE(slice_begin % 256 == 0 && slice_end % 256 == 0 && slice_begin <= slice_end, "adamw_peer: slice [%lld, %lld) must be 256-aligned",
                (long long)slice_begin, (long long)slice_end);
@@ -302,6 +325,17 @@ int adamw_peer_step(const float* const* grad_ptrs, float* const* param_ptrs, int
   adamw_peer_kernel<W_, U_><<<blocks, 256, 0, st>>>(pp, m, v, p16, decay_chunk, slice_begin / 4, slice_end / 4, clean_begin / 4, \
                                                     clean_end / 4, keep_b, keep_e, c, pp.param[rank], const_cast<float*>(pp.grad[rank]),  \
                                                     hyper_dev, t)
+  if (mc_grad != nullptr && mc_param != nullptr && world > 1) {
+    const float* my_p = pp.param[rank];
+    const float* my_g = pp.grad[rank];
+    pp.grad[0] = mc_grad;                       // multicast form: slot 0 carries the multicast addresses,
+    pp.param[0] = mc_param;
+    adamw_peer_kernel<0, 4><<<blocks, 256, 0, st>>>(pp, m, v, p16, decay_chunk, slice_begin / 4, slice_end / 4, clean_begin / 4,
+                                                    clean_end / 4, keep_b, keep_e, c, my_p, const_cast<float*>(my_g), hyper_dev, t);
+    MAGB_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+  }
   switch (world) {
     case 1: MAGB_PEER_LAUNCH(1, 4); break;
     case 2: MAGB_PEER_LAUNCH(2, 4); break;

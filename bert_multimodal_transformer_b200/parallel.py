@@ -113,6 +113,16 @@ class PeerMemory:
                 return arr
         raise KeyError("tensor was not allocated through this PeerMemory")
 
+    def multicast_pointer(self, tensor):
+        """NVSwitch multicast address of `tensor` (allocated by self.empty), or 0 when the node / allocator has none."""
+        for t, h in self._keep:
+            if t.data_ptr() == tensor.data_ptr():
+                try:
+                    return int(h.multicast_ptr or 0)
+                except Exception:        # pragma: no cover  (older allocator without the attribute)
+                    return 0
+        raise KeyError("tensor was not allocated through this PeerMemory")
+
     def owned_slice(self, total):
         """256-aligned [begin, end) of a flat buffer of `total` elements (a multiple of 256) that this rank updates."""
         chunks = total // 256

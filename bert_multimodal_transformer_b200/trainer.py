@@ -82,6 +82,11 @@ class MagBertTrainer:
             self.peer_grad_ptrs = self.peer.pointers(self.grads)
             self.peer_param_ptrs = self.peer.pointers(eng.flat)
             self.peer_slice = self.peer.owned_slice(n)
+            # NVSwitch multicast addresses of the two buffers (0 when the allocator has no multicast object for them)
+            use_mc = os.environ.get("MAGB200_PEER_MULTICAST", "0") == "1"
+            mg, mp = (self.peer.multicast_pointer(self.grads), self.peer.multicast_pointer(eng.flat)) if use_mc else (0, 0)
+            self.peer_mc_grad = ctypes.c_void_p(mg) if mg and mp else None
+            self.peer_mc_param = ctypes.c_void_p(mp) if mg and mp else None
             self.peer_blocks = int(os.environ.get("MAGB200_PEER_ADAMW_BLOCKS", "0"))
             self.peer_overlap = os.environ.get("MAGB200_PEER_OVERLAP", "0") == "1"
             self.peer_lazy_clear = os.environ.get("MAGB200_PEER_LAZY_CLEAR", "0") == "1"   # measured slower (4.20 vs 4.16 ms at 2 GPUs)
@@ -223,7 +228,8 @@ class MagBertTrainer:
                                             clean[0], clean[1], self.lr, self.betas[0], self.betas[1], self.eps, self.wd, 1,
                                             grad_unscale(self.world), L.ptr(self.dev_hyper),
                                             self.peer_blocks if blocks is None else blocks, *table,
-                                            1 if self.peer_lazy_clear else 3, keep[0], keep[1], stream_handle))
+                                            1 if self.peer_lazy_clear else 3, keep[0], keep[1], self.peer_mc_grad,
+                                            self.peer_mc_param, stream_handle))
 
     def _peer_barrier(self, stream_handle):
         pm = self.peer

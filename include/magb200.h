@@ -232,7 +232,8 @@ typedef struct magb200_bert_dims {
  * magb200_adamw_peer_step: for the 256-aligned slice [slice_begin, slice_end) this rank owns -- sums the gradients of all
  * ranks in rank order (P2P loads), applies the transformers-3.0.2 AdamW of magb200_adamw_step to its local moments, and
  * stores the updated parameters into every rank's buffer (P2P stores) plus the local fp16 mirror: reduce-scatter + AdamW +
- * all-gather in one kernel; max_blocks > 0 bounds the grid (SMs left to concurrent GEMMs).  [clean_begin, clean_end) is a
+ * all-gather in one kernel (with multicast_grad / multicast_param non-NULL -- the NVSwitch multicast addresses of the two
+ * buffers -- the sum is a multimem.ld_reduce inside the switch and the broadcast one multimem.st); max_blocks > 0 bounds the grid (SMs left to concurrent GEMMs).  [clean_begin, clean_end) is a
  * range all ranks finished earlier (a barrier lies between): its local gradients are cleared and the parameters the peers
  * stored into it are recast into the local fp16 mirror (empty range: nothing; clean_what bit 0 = recast, bit 1 = clear;
  * [keep_begin, keep_end) inside it is not recast -- the caller's own piece, whose mirror its update wrote).
@@ -245,7 +246,8 @@ int magb200_adamw_peer_step(const void* const* grad_ptrs, void* const* param_ptr
                             int64_t clean_begin, int64_t clean_end, float lr, float beta1, float beta2, float eps,
                             float weight_decay, int step, float grad_unscale, const float* hyper_dev, int max_blocks,
                             const uint8_t* row_any, int row_mode, int64_t table_begin, int table_rows, int row_len,
-                            int clean_what, int64_t keep_begin, int64_t keep_end, void* stream);
+                            int clean_what, int64_t keep_begin, int64_t keep_end, const void* multicast_grad,
+                            void* multicast_param, void* stream);
 /* Row-sparse table inside a bucket (the word-embedding matrix, bert.py:211 / nn.Embedding backward: only the rows of the
  * step's token ids receive a gradient).  magb200_peer_mark_rows stamps marks[id] (uint32[vocab] in symmetric memory) for
  * the batch's ids with (*counter + 1) and advances the device counter; after a barrier magb200_peer_combine_marks writes

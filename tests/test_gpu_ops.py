@@ -567,7 +567,7 @@ def test_peer_optimizer_kernel_equals_allreduce_then_adamw(world):
             L.check(lib().magb200_adamw_peer_step(gp, pp, world, 0, L.ptr(m), L.ptr(v), L.ptr(p16), L.ptr(decay), owned[0],
                                                   owned[1], clean[0], clean[1], lr, b1, b2, eps, wd, 2, 1.0 / world, None, 0,
                                                   L.ptr(any_rows) if mode else None, mode, 0, rows if mode else 0,
-                                                  H if mode else 0, 3, 0, 0, stream()))
+                                                  H if mode else 0, 3, 0, 0, None, None, stream()))
         if sparse:
             L.check(lib().magb200_peer_mark_rows(L.ptr(ids), ids.numel(), rows, L.ptr(marks), L.ptr(counter), stream()))
             L.check(lib().magb200_peer_combine_marks(_ptr_array(*([marks] * world)), world, L.ptr(counter), rows,

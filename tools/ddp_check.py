@@ -41,7 +41,8 @@ def note(msg):
 model = make()
 note("model built")
 tr = MagBertTrainer(model, GLOBAL_B // world, 50, lr=1e-4, weight_decay=0.01, total_steps=0, use_cuda_graph=True)
-note(f"trainer built (peer-memory optimizer: {getattr(tr, 'peer', None) is not None})")
+note(f"trainer built (peer-memory optimizer: {getattr(tr, 'peer', None) is not None}, "
+     f"multicast: {getattr(tr, 'peer_mc_grad', None) is not None})")
 losses = [tr.train_step(*args(mine)) for _ in range(STEPS)]
 torch.cuda.synchronize()
 note(f"steps done, losses {losses}")

@@ -72,7 +72,9 @@ mx = acc.clone()
 dist.all_reduce(mx, op=dist.ReduceOp.MAX)
 if rank == 0:
     own = own * 4 / 1e6
-    print(f"world {world}: owned slice {own:.1f} MB of {total * 4 / 1e6:.1f} MB; eager launches, ms (max over ranks / rank 0):")
+    print(f"world {world}: owned slice {own:.1f} MB of {total * 4 / 1e6:.1f} MB; "
+          f"NVSwitch multicast {'on' if tr.peer_mc_grad is not None else 'off'}; "
+          f"eager launches, ms (max over ranks / rank 0):")
     for n, a, m in zip(names, acc.tolist(), mx.tolist()):
         print(f"  {n:34s} {m:8.3f} {a:8.3f}")
     k = mx[3].item()
