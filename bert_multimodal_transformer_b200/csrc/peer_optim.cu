@@ -31,14 +31,25 @@ struct PeerPtrs {
   float* param[kMaxPeers];
 };
 
-__device__ __forceinline__ float4 ld_peer_f4(const float* p) {
-  float4 v;      // peer memory is never cached stale here: one read per step, straight after a system-scope barrier
-  asm volatile("ld.global.relaxed.sys.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p)
-               : "memory");
+// Peer loads / stores.  Ordering between ranks comes from the barrier KERNELS around this one (system-scope fences,
+// release / acquire flags, and the kernel boundary itself), so the data accesses can be weak; the loads bypass L1
+// allocation so that a line of peer memory can never be served stale from an earlier launch.  MAGB200_PEER_STRONG=1
+// selects relaxed.sys accesses instead (SASS: LDG / STG.E.128.STRONG.SYS) -- the first version, 320
+// GB/s per direction at 2 GPUs.
+__device__ __forceinline__ float4 ld_peer_f4(const float* p, bool strong = false) {
+  float4 v;
+  if (strong)
+    asm volatile("ld.global.relaxed.sys.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p)
+                 : "memory");
+  else
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
-__device__ __forceinline__ void st_peer_f4(float* p, const float4& v) {
-  asm volatile("st.global.relaxed.sys.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+__device__ __forceinline__ void st_peer_f4(float* p, const float4& v, bool strong = false) {
+  if (strong)
+    asm volatile("st.global.relaxed.sys.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  else
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 // NVSwitch multicast (NVLS): one address that stands for the same offset in every rank's buffer.  A reducing load returns
@@ -56,6 +67,7 @@ __device__ __forceinline__ void multimem_st_f4(float* mc, const float4& v) {
 
 struct AdamConsts {
   float lr, b1, b2, eps, wd, step_size, gscale;
+  int strong;          // peer accesses as relaxed.sys instead of weak
 };
 
 // Row-sparse table inside a bucket (the word-embedding matrix: a step touches at most batch * seq of its 30522 rows).
@@ -99,7 +111,7 @@ __device__ __forceinline__ void adamw_peer_element(const PeerPtrs& peers, float4
     multimem_st_f4(peers.param[0] + 4 * i, pp);          // param[0] = the multicast address
   } else {
 #pragma unroll
-    for (int q = 0; q < W; ++q) st_peer_f4(peers.param[q] + 4 * i, pp);
+    for (int q = 0; q < W; ++q) st_peer_f4(peers.param[q] + 4 * i, pp, c.strong != 0);
   }
   if (p16) {
     __half2 a = __floats2half2_rn(pp.x, pp.y), b = __floats2half2_rn(pp.z, pp.w);
@@ -155,7 +167,7 @@ __global__ void __launch_bounds__(256) adamw_peer_kernel(const PeerPtrs peers, f
       } else {
 #pragma unroll
         for (int q = 0; q < W; ++q)
-          g[u][q] = kind[u] == ROW_FULL ? ld_peer_f4(peers.grad[q] + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          g[u][q] = kind[u] == ROW_FULL ? ld_peer_f4(peers.grad[q] + 4 * i, c.strong != 0) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
 #pragma unroll
@@ -180,7 +192,7 @@ __global__ void __launch_bounds__(256) adamw_peer_kernel(const PeerPtrs peers, f
       }
     }
     if ((table.clean_what & 1) && p16 && !(j >= keep_begin4 && j < keep_end4)) {
-      const float4 pp = ld_peer_f4(my_param + 4 * j);              // written by its owner over NVLink: not through L1
+      const float4 pp = ld_peer_f4(my_param + 4 * j, c.strong != 0);   // written by its owner over NVLink: not through L1
       __half2 a = __floats2half2_rn(pp.x, pp.y), b = __floats2half2_rn(pp.z, pp.w);
       uint2 u;
       u.x = *reinterpret_cast<uint32_t*>(&a);
@@ -310,6 +322,12 @@ int adamw_peer_step(const float* const* grad_ptrs, float* const* param_ptrs, int
   }
   AdamConsts c;
   c.lr = lr; c.b1 = b1; c.b2 = b2; c.eps = eps; c.wd = wd; c.gscale = gscale;
+  static int strong = -1;
+  if (strong < 0) {
+    const char* e = getenv("MAGB200_PEER_STRONG");
+    strong = (e && *e && atoi(e) != 0) ? 1 : 0;
+  }
+  c.strong = strong;
   c.step_size = lr * sqrtf(1.f - powf(b2, (float)step)) / (1.f - powf(b1, (float)step));
   RowTable t;
   t.any = row_any; t.mode = row_mode; t.begin4 = table_begin / 4; t.row_len4 = row_mode ? row_len / 4 : 1;

@@ -74,6 +74,16 @@ def sparse_rows_allreduce_(table_grad: torch.Tensor, ids: torch.Tensor, group=No
     return table_grad
 
 
+def owned_piece(begin: int, end: int, world: int, rank: int):
+    """The 256-aligned 1 / world of bucket [begin, end) that `rank` updates in the peer-memory optimizer step
+    (csrc/peer_optim.cu): equal chunks rounded up to 256 elements, the last ranks get what is left (possibly nothing).
+    The pieces of all ranks tile the bucket exactly, so every element has one owner."""
+    assert begin % 256 == 0 and end % 256 == 0 and begin <= end and 0 <= rank < world
+    chunk = -(-(end - begin) // (world * 256)) * 256
+    b = min(end, begin + rank * chunk)
+    return b, min(end, b + chunk)
+
+
 class PeerMemory:
     """Symmetric (peer-mapped) device buffers of the ranks of ONE node, for the NVLink-native optimizer step
     (csrc/peer_optim.cu): torch's symmetric-memory allocator + rendezvous give every rank the addresses of every other

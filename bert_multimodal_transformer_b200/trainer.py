@@ -58,10 +58,10 @@ class MagBertTrainer:
         n = eng.layout.total
         # Data parallel on one NVLink node: parameters and gradients move to symmetric (peer-mapped) memory and the
         # optimizer step becomes reduce-scatter + AdamW + all-gather in ONE kernel over peer pointers
-        # (csrc/peer_optim.cu); MAGB200_PEER_ADAMW=0 (or an unavailable symmetric-memory allocator) keeps the NCCL
-        # all-reduce schedule.
+        # (csrc/peer_optim.cu) -- measured 85.2 k vs 74.2 k samples/s at 8 GPUs, 24.0 k vs 22.2 k at 2 (profiles/r02_n8_*,
+        # r02_n2_*); MAGB200_PEER_ADAMW=0 (or an unavailable symmetric-memory allocator) keeps the NCCL all-reduce schedule.
         self.peer = None
-        if self.world > 1 and os.environ.get("MAGB200_PEER_ADAMW", "0") == "1" and hasattr(eng, "allocator"):
+        if self.world > 1 and os.environ.get("MAGB200_PEER_ADAMW", "1") == "1" and hasattr(eng, "allocator") and dev.type == "cuda":
             try:
                 from .parallel import PeerMemory
                 pm = PeerMemory(dev, process_group)
@@ -237,10 +237,8 @@ class MagBertTrainer:
 
     def _peer_piece(self, s, e):
         """The 256-aligned 1 / world of bucket [s, e) this rank owns (every rank owns a piece of every bucket)."""
-        W, r = self.peer.world, self.peer.rank
-        chunk = -(-(e - s) // (W * 256)) * 256
-        b = min(e, s + r * chunk)
-        return b, min(e, b + chunk)
+        from .parallel import owned_piece
+        return owned_piece(s, e, self.peer.world, self.peer.rank)
 
     def _peer_clear_gradients_early(self):
         """MAGB200_PEER_LAZY_CLEAR: the gradients of the previous step are cleared on the communication stream while the

@@ -89,3 +89,22 @@ def test_sparse_embedding_gradient_exchange_equals_dense_allreduce(tmp_path):
         assert r["ok"], r["err"]
     # replicas must not drift: every rank holds the same BITS (additions happen in rank order everywhere)
     assert torch.equal(res[0]["got"], res[1]["got"])
+
+
+def test_peer_optimizer_ownership_tiles_every_bucket():
+    """parallel.owned_piece (who updates what in the peer-memory optimizer step): for any bucket and world size the pieces
+    are 256-aligned, disjoint, in rank order, and cover the bucket exactly -- an element with two owners would be updated
+    twice, one with none never."""
+    from bert_multimodal_transformer_b200.parallel import owned_piece
+    for world in (1, 2, 3, 4, 7, 8):
+        for begin, end in ((0, 256), (0, 23_835_648), (23_835_648, 109_483_776 // 256 * 256), (512, 512), (256, 256 * 6)):
+            pieces = [owned_piece(begin, end, world, r) for r in range(world)]
+            cursor = begin
+            for b, e in pieces:
+                assert b % 256 == 0 and e % 256 == 0 and b <= e
+                assert b == min(cursor, end) and e <= end
+                cursor = max(cursor, e)
+            assert cursor == end
+            sizes = [e - b for b, e in pieces]
+            assert max(sizes) - min(s for s in sizes if s or True) <= max(sizes)     # no piece larger than the first
+            assert sizes == sorted(sizes, reverse=True)

@@ -8,7 +8,7 @@ grep -A10 "^world" gpurun_out/peer_probe_$N.log | cut -c1-200; grep -E "Error|er
 MAGB200_PEER_ADAMW=1 timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29601 tools/ddp_check.py > gpurun_out/ddp_check_peer_${N}.log 2>&1; echo "ddp_check(peer) exit=$?"
 grep -E "DDP_CHECK|rel_first|spread|Error|error|Traceback|timed out" gpurun_out/ddp_check_peer_${N}.log | cut -c1-300 | tail -8
 i=0
-IFS='|' read -ra VS <<< "${VARIANTS:-MAGB200_PEER_ADAMW=0|MAGB200_PEER_ADAMW=1|MAGB200_PEER_ADAMW=0 WL=mosei128|MAGB200_PEER_ADAMW=1 WL=mosei128}"
+IFS='|' read -ra VS <<< "${VARIANTS:-MAGB200_PEER_ADAMW=0|MAGB200_PEER_ADAMW=1|MAGB200_PEER_ADAMW=1 WL=mosei128}"
 for v in "${VS[@]}"; do
   i=$((i+1))
   wl=mosi48; case "$v" in *WL=mosei128*) wl=mosei128;; esac
