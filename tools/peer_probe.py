@@ -78,8 +78,10 @@ if rank == 0:
     for n, a, m in zip(names, acc.tolist(), mx.tolist()):
         print(f"  {n:34s} {m:8.3f} {a:8.3f}")
     k = mx[3].item()
-    print(f"  kernel: {(world - 1) * own / k:.1f} GB/s NVLink in (and out) per GPU, "
-          f"{(own * 7 + own * 0.5) / k:.1f} GB/s local HBM")
+    # each direction of a GPU's NVLink carries the gradients it pulls (in) / serves (out) AND the parameters it receives
+    # (in) / stores (out): 2 (W-1)/W of the model per direction
+    print(f"  kernel: {2 * (world - 1) * own / k:.1f} GB/s per NVLink direction per GPU "
+          f"(gradient pulls + parameter stores), {(own * 7 + own * 0.5) / k:.1f} GB/s local HBM")
 dist.barrier()
 torch.cuda.synchronize()
 os._exit(0)
