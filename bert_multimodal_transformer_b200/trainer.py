@@ -84,10 +84,11 @@ class MagBertTrainer:
             self.peer_slice = self.peer.owned_slice(n)
             # NVSwitch multicast addresses of the two buffers (0 when the allocator has no multicast object for them)
             # NVLink bytes per direction and GPU: peer loads / stores 2 (W-1)/W of the model, multicast (W+1)/W (own data
-            # loops through the switch): worse at 2 GPUs (measured 1.17 vs 0.69 ms for the kernel), better from 4 up.
-            # "auto" = from 4 GPUs; the default stays "0" until the form has run at 8 GPUs.
-            mc_env = os.environ.get("MAGB200_PEER_MULTICAST", "0")
-            use_mc = mc_env == "1" or (mc_env == "auto" and self.world >= 4)
+            # loops through the switch): worse at 2 GPUs (kernel 1.17 vs 0.69 ms), better at 8 (0.99 vs 1.19 ms, step 4.33
+            # vs 4.51 ms; profiles/r02_peer_probe_n8*.txt).  "auto" (default) = from 6 GPUs up, where it has been run;
+            # "1" / "0" force it on / off.  Without a multicast object for the buffers the peer-pointer form is used.
+            mc_env = os.environ.get("MAGB200_PEER_MULTICAST", "auto")
+            use_mc = mc_env == "1" or (mc_env == "auto" and self.world >= 6)
             mg, mp = (self.peer.multicast_pointer(self.grads), self.peer.multicast_pointer(eng.flat)) if use_mc else (0, 0)
             self.peer_mc_grad = ctypes.c_void_p(mg) if mg and mp else None
             self.peer_mc_param = ctypes.c_void_p(mp) if mg and mp else None
