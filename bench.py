@@ -362,6 +362,18 @@ def class_api_loop(torch, model, batch, device, steps, warmup, total_steps):
     return time.perf_counter() - t0, last, optimizer.fused_steps_taken
 
 
+def gradient_exchange(trainer, world):
+    """what moves the gradients at world > 1, for the bench line's config block"""
+    if world == 1:
+        return "none (one GPU)"
+    if getattr(trainer, "peer", None) is None:
+        return "NCCL all-reduce per layer group + AdamW of the slice behind backward, (ids, rows) exchange for the embedding table"
+    via = "NVSwitch multicast (multimem.ld_reduce / multimem.st)" if getattr(trainer, "peer_mc_grad", None) is not None \
+        else "NVLink peer pointers"
+    return ("peer-memory optimizer step: reduce-scatter + AdamW + all-gather in one kernel per bucket over " + via +
+            ", optimizer state sharded, embedding table by touched rows; no collective library on the data path")
+
+
 def run_gpu_arm(args, wl):
     import torch
     import torch.distributed as dist
@@ -540,7 +552,7 @@ def run_gpu_arm(args, wl):
         "config": {"workload": wl["desc"], "global_batch": BS * world, "seq_len": SEQ, "parallelism": f"dp{world}",
                    "l2": "no flush needed: each step streams ~2.5 GB (params, grads, Adam moments, activations) "
                          ">> 126 MB L2",
-                   "cuda_graph": trainer.use_graph},
+                   "cuda_graph": trainer.use_graph, "gradient_exchange": gradient_exchange(trainer, world)},
         "clocks": clk.summary(),
         "e2e": {"value": round(e2e_value, 1), "unit": "samples/s", "h2d_bytes_per_step": trainer.h2d_bytes,
                 "d2h_bytes_per_step": trainer.d2h_bytes, "ms_per_step": round(ms_e2e / args.steps, 4),
