@@ -3,7 +3,8 @@
 
 Counts, per kernel, the SASS mnemonics that prove which hardware path a kernel uses (B200_PROFILING.md):
 UTC*MMA = tcgen05.mma, LDTM/STTM = tcgen05.ld/st, UTMALDG = TMA load, UTMAREDG = TMA reduce, UTCBAR = tcgen05.commit,
-HMMA = mma.sync (legacy tensor path), LDSM = ldmatrix, LDGSTS = cp.async, UCGABAR = cluster barrier."""
+HMMA = mma.sync (legacy tensor path), LDSM = ldmatrix, LDGSTS = cp.async, UCGABAR = cluster barrier,
+LDGMC = multimem.ld_reduce (NVSwitch multicast reducing load)."""
 import collections
 import re
 import subprocess
@@ -13,7 +14,7 @@ txt = sys.stdin.read()
 funcs = re.split(r"\n\s*Function : ", txt)
 pat = re.compile(r"\b(UTCHMMA[A-Z0-9.]*|UTCQMMA[A-Z0-9.]*|UTMALDG[A-Z0-9.]*|UTMAREDG[A-Z0-9.]*|UTMASTG[A-Z0-9.]*|UBLKCP[A-Z0-9.]*|"
                  r"UBLKRED[A-Z0-9.]*|LDTM[A-Z0-9]*|STTM[A-Z0-9]*|UTCBAR[A-Z0-9.]*|HMMA[A-Z0-9.]*|LDSM[A-Z0-9.]*|LDGSTS[A-Z0-9.]*|"
-                 r"UCGABAR_[A-Z]*|REDG?\.E[A-Z0-9.]*)")
+                 r"UCGABAR_[A-Z]*|REDG?\.E[A-Z0-9.]*|LDGMC[A-Z0-9.x]*)")
 rows = []
 for f in funcs[1:]:
     name = f.split("\n")[0].strip()
