@@ -91,6 +91,27 @@ def _check_supported(config):
         raise NotImplementedError("decoder / cross-attention path (bert.py:186-201) is not on the MAG hot path")
 
 
+def _is_default_position_ids(position_ids, seq_len):
+    """True when position_ids is None or spells out the default 0 .. seq_len-1 for every row ([S], [1, S] or [B, S])."""
+    if position_ids is None:
+        return True
+    p = torch.as_tensor(position_ids)
+    if p.dim() == 0 or p.shape[-1] != seq_len or p.dim() > 2:
+        return False
+    want = torch.arange(seq_len, device=p.device, dtype=p.dtype)
+    return bool((p == want).all())
+
+
+def _is_identity_head_mask(head_mask):
+    """True when head_mask keeps every head: None, a list of None, or a tensor / list of tensors of ones."""
+    if head_mask is None:
+        return True
+    if isinstance(head_mask, (list, tuple)):
+        return all(_is_identity_head_mask(h) for h in head_mask)
+    h = torch.as_tensor(head_mask)
+    return bool((h == 1).all())
+
+
 class MAG_BertModel(nn.Module):
     """bert.py:76-237.  Holds embeddings / encoder / pooler / MAG parameters."""
 
@@ -239,14 +260,20 @@ class MAG_BertForSequenceClassification(nn.Module):
             raise ValueError("You cannot specify both input_ids and inputs_embeds at the same time")
         if input_ids is None and inputs_embeds is None:
             raise ValueError("You have to specify either input_ids or inputs_embeds")
-        if inputs_embeds is not None or position_ids is not None or head_mask is not None:
-            raise NotImplementedError("inputs_embeds / position_ids / head_mask are not supported by the native path")
+        if inputs_embeds is not None:
+            raise NotImplementedError("inputs_embeds is not supported by the native path (the embedding kernels gather by id)")
         self._ensure_bound()
         eng = self._engine
         dev = eng.flat.device
         ids, vis, aco, mask, tt = prep_inputs(dev, input_ids, visual, acoustic, attention_mask, token_type_ids)
         if ids.dim() != 2 or vis.shape[:2] != ids.shape or aco.shape[:2] != ids.shape:
             raise ValueError("input_ids [B,S], visual [B,S,V], acoustic [B,S,A] expected")
+        # Values that mean "the default" are accepted like the reference accepts them (bert.py:147-156 builds arange
+        # positions, bert.py:208-209 turns head_mask=None into [None] * layers); anything else has no kernel.
+        if not _is_default_position_ids(position_ids, ids.shape[-1]):
+            raise NotImplementedError("position_ids other than arange(seq_len) are not supported by the native path")
+        if not _is_identity_head_mask(head_mask):
+            raise NotImplementedError("a head_mask other than None / all ones is not supported by the fused attention kernels")
         if vis.shape[-1] != eng.visual_dim or aco.shape[-1] != eng.acoustic_dim:
             raise ValueError(f"visual/acoustic feature dims {vis.shape[-1]}/{aco.shape[-1]} do not match the model "
                              f"({eng.visual_dim}/{eng.acoustic_dim})")

@@ -174,3 +174,22 @@ def test_state_dict_keys_equal_the_reference_models():
     assert set(m.state_dict()) == set(weights.bert_state_dict(num_layers=2))
     # reference init (bert.py:90,249): N(0, 0.02) weights, zero biases, unit LayerNorm -- MAG included
     assert abs(m.bert.MAG.W_hv.weight.std().item() - 0.02) < 2e-3 and m.bert.MAG.W_hv.bias.abs().max().item() == 0
+
+
+def test_default_valued_extras_are_recognised():
+    """bert.py:147-156 / 208-209: position_ids=None means arange, head_mask=None means 'keep every head'.  The native
+    path accepts exactly the values that mean the same thing and refuses the rest (no kernel for them)."""
+    from bert_multimodal_transformer_b200.bert import _is_default_position_ids, _is_identity_head_mask
+    assert _is_default_position_ids(None, 50)
+    assert _is_default_position_ids(torch.arange(50), 50)
+    assert _is_default_position_ids(torch.arange(50).unsqueeze(0).expand(4, 50), 50)
+    assert not _is_default_position_ids(torch.arange(50).flip(0), 50)
+    assert not _is_default_position_ids(torch.arange(49), 50)
+    assert not _is_default_position_ids(torch.zeros(2, 3, 50, dtype=torch.long), 50)
+    assert _is_identity_head_mask(None)
+    assert _is_identity_head_mask([None] * 12)
+    assert _is_identity_head_mask(torch.ones(12, 12))
+    assert _is_identity_head_mask([torch.ones(12)] * 12)
+    m = torch.ones(12, 12)
+    m[3, 5] = 0
+    assert not _is_identity_head_mask(m)

@@ -181,13 +181,21 @@ def test_api_contract_and_errors():
         model(None, cb["visual"], cb["acoustic"])
     with pytest.raises(ValueError, match="cannot specify both"):
         model(cb["input_ids"], cb["visual"], cb["acoustic"], inputs_embeds=torch.zeros(2, 50, 768))
+    pruned = torch.ones(1, 12)
+    pruned[0, 3] = 0.0
     with pytest.raises(NotImplementedError):
-        model(cb["input_ids"], cb["visual"], cb["acoustic"], head_mask=torch.ones(1, 12))
+        model(cb["input_ids"], cb["visual"], cb["acoustic"], head_mask=pruned)
+    with pytest.raises(NotImplementedError):
+        model(cb["input_ids"], cb["visual"], cb["acoustic"], position_ids=torch.arange(50, device="cuda").flip(0))
     with torch.no_grad():
         a = model(cb["input_ids"], cb["visual"], cb["acoustic"])[0]                       # default mask / segments
         ones = torch.ones_like(cb["input_ids"])
         b = model(cb["input_ids"], cb["visual"], cb["acoustic"], ones, torch.zeros_like(ones))[0]   # positional order
+        # values that spell out the defaults (bert.py:147-156, 208-209) are accepted and change nothing
+        c = model(cb["input_ids"], cb["visual"], cb["acoustic"], position_ids=torch.arange(50, device="cuda"),
+                  head_mask=torch.ones(1, 12))[0]
     assert torch.equal(a, b)
+    assert torch.equal(a, c)
     # parameters keep the reference's names and weight-decay grouping works (multimodal_driver.py:328-343)
     names = [n for n, _ in model.named_parameters()]
     assert "bert.MAG.W_hv.weight" in names and "classifier.bias" in names
