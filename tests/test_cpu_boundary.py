@@ -193,3 +193,24 @@ def test_default_valued_extras_are_recognised():
     m = torch.ones(12, 12)
     m[3, 5] = 0
     assert not _is_identity_head_mask(m)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU oracle arm the driver runs next to ours): one JSON line with the arm's keys,
+    same metric / unit / workload string as the GPU arm, zero transfers and launches."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "samples/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    import bench
+    assert d["metric"] == bench.WORKLOADS["mosi48"]["metric"] and d["config"]["workload"] == bench.WORKLOADS["mosi48"]["desc"]
