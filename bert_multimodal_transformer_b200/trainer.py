@@ -5,12 +5,14 @@ forward, MSE loss, backward, AdamW step, LR-schedule step, zero_grad, `loss.item
 the whole step is ~1.3 TFLOP spread over ~300 kernels, so launch latency dominates unless the step
 is replayed as one graph.  `MagBertTrainer.train_step` does exactly that:
 
-    pinned host batch --H2D--> [ forward | mse | backward | (NCCL all-reduce) | AdamW+zero_grad+fp16 refresh ] --D2H--> loss
+    pinned host batch --H2D--> [ forward | mse | backward | gradient exchange | AdamW+zero_grad+fp16 refresh ] --D2H--> loss
 
 Everything that changes from step to step (dropout seed, learning rate, Adam bias correction) is read
 by the kernels from a small device control block that is part of the H2D copy, so one captured graph
 serves every step.  Data parallelism: one process per GPU, each rank runs this on
-its own slice of the batch; the only collective is the gradient all-reduce over the flat buffer.
+its own slice of the batch.  Gradient exchange and update at world > 1 are, by default, ONE kernel per bucket over
+NVLink peer memory (reduce-scatter + AdamW on the owned 1/world + all-gather of the parameters, csrc/peer_optim.cu,
+_peer_step below); the NCCL all-reduce schedule (_backward_overlapped) is the fallback.  DESIGN.md section 6.
 """
 from __future__ import annotations
 
