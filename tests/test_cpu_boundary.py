@@ -214,3 +214,27 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     import bench
     assert d["metric"] == bench.WORKLOADS["mosi48"]["metric"] and d["config"]["workload"] == bench.WORKLOADS["mosi48"]["desc"]
+
+
+def test_documents_cite_files_that_exist():
+    """DESIGN.md / INTEGRATION.md / README.md / profiles/README.md / tools/README.md name evidence and source files in back-ticks;
+    a citation of a file that is not in the tree is a claim without evidence."""
+    import glob
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    missing = []
+    for doc in ("DESIGN.md", "INTEGRATION.md", "README.md", os.path.join("profiles", "README.md"), os.path.join("tools", "README.md")):
+        with open(os.path.join(root, doc)) as fh:
+            text = fh.read()
+        for tok in set(re.findall(r"`([^`\n]+)`", text)):
+            t = tok.strip().split("::")[0]
+            if re.match(r"^(profiles/)?r0\d_[A-Za-z0-9_.*-]+$", t):
+                path = t if t.startswith("profiles/") else "profiles/" + t
+            elif re.match(r"^(tools|tests|oracle|include|profiles|bert_multimodal_transformer_b200)/[A-Za-z0-9_./*-]+$", t):
+                path = t
+            else:
+                continue
+            if path.endswith(".*"):
+                path = path[:-2] + "*"
+            if not glob.glob(os.path.join(root, path)) and not glob.glob(os.path.join(root, path + "*")):
+                missing.append((doc, tok))
+    assert not missing, missing
