@@ -107,3 +107,42 @@ def test_peer_optimizer_ownership_tiles_every_bucket():
             assert cursor == end
             sizes = [e - b for b, e in pieces]
             assert sizes == sorted(sizes, reverse=True)
+
+
+def test_peer_step_schedule_equals_allreduce_then_adamw():
+    """oracle/peer_step.py restates the schedule of the peer-memory optimizer step (ownership by bucket piece, early pass over
+    the embedding rows nobody touched, late pass over the rest, parameters copied from the owner).  Over several steps with
+    changing batches it must equal the textbook data-parallel step -- mean gradient on every rank, then transformers-3.0.2
+    AdamW on the full vector -- and keep the replicas bit-identical.  Untouched rows really have zero gradient here, as in
+    the embedding backward."""
+    from oracle import peer_step as PS
+    g = torch.Generator().manual_seed(5)
+    rows, rl, extra = 37, 64, 256 * 9 + 0
+    table_elems = rows * rl
+    n = (table_elems + 255) // 256 * 256 + extra
+    lr, b1, b2, eps, wd = 1e-3, 0.9, 0.999, 1e-6, 0.01
+    decay = (torch.rand(n, generator=g) > 0.3).float()
+    for world in (1, 2, 3, 8):
+        p0 = torch.randn(n, generator=g)
+        params = [p0.clone() for _ in range(world)]
+        moments = [(torch.zeros(n), torch.zeros(n)) for _ in range(world)]
+        ref_p, ref_m, ref_v = p0.clone(), torch.zeros(n), torch.zeros(n)
+        for step in (1, 2, 3, 4):
+            ids = [torch.randint(0, rows, (2, 5), generator=g) for _ in range(world)]
+            grads = []
+            for r in range(world):
+                gr = torch.randn(n, generator=g) * 0.01
+                hit = torch.zeros(rows, dtype=torch.bool)
+                hit[ids[r].reshape(-1)] = True
+                gr[:table_elems].view(rows, rl)[~hit] = 0.0            # nn.Embedding backward: only the batch's rows
+                gr[table_elems:(table_elems + 255) // 256 * 256] = 0.0  # alignment padding carries nothing
+                grads.append(gr)
+            mean = sum(grads) / world
+            PS.adamw_(ref_p, mean, ref_m, ref_v, decay, lr, b1, b2, eps, wd, step)
+            PS.peer_step(params, grads, moments, decay, (0, rows, rl), ids, lr, b1, b2, eps, wd, step)
+            for q in range(1, world):
+                assert torch.equal(params[q], params[0])
+            assert (params[0] - ref_p).abs().max().item() < 2e-6, (world, step)
+            assert all(float(gr.abs().max()) == 0.0 for gr in grads)
+        gathered_m = sum(m for m, _ in moments)                        # every element has exactly one owner
+        assert (gathered_m - ref_m).abs().max().item() < 1e-7
